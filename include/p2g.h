@@ -1,0 +1,161 @@
+/*
+ * p2g.h -- C ABI of the B200 polynomial-commitment library (libp2g_cuda.so).
+ *
+ * This is the drop-in boundary for ONE hot path of telosnetwork/plonky2_goldibear: the bodies of
+ *   PolynomialBatch::from_values   plonky2/src/fri/oracle.rs:68-90
+ *   PolynomialBatch::from_coeffs   plonky2/src/fri/oracle.rs:93-123
+ *   MerkleTree::new                plonky2/src/hash/merkle_tree.rs:152-181
+ * The reference has no FFI layer; under its (new) `cuda` cargo feature those three functions bind the entry
+ * points below (INTEGRATION.md shows the Rust side).  Plain pointers and sizes only; no torch types.
+ *
+ * Everything here runs on the GPU: there is NO CPU fallback.  If no CUDA device is usable p2g_init fails
+ * and every other call returns P2G_ERR_NO_DEVICE.
+ *
+ * Element conventions
+ *   Goldilocks : uint64_t.  Any value accepted on input (treated mod p); outputs canonical (< p).
+ *   BabyBear   : uint32_t.  `repr` selects canonical integers or p3-monty-31's in-memory Montgomery form
+ *                (R = 2^32; 1 <-> 268435454); outputs use the same representation as the inputs.
+ *   Digest     : 32 bytes = 4 Goldilocks or 8 BabyBear elements (HashOut, hash/hash_types.rs:105-108), stored as
+ *                elements in the field's representation.
+ * Layouts
+ *   columns    : column-major, one contiguous array of n = 2^log_n elements per polynomial (mirrors
+ *                Vec<PolynomialValues<F>> / Vec<PolynomialCoeffs<F>>).
+ *   leaves     : row-major [N][leaf_pitch] with N = n << rate_bits rows; row k holds the evaluations at
+ *                g * w_N^{bitrev_N(k)} of every polynomial, then the salt columns (oracle.rs:108-109,153-158).
+ *   digests    : 2*(N - 2^cap_height) digests in the reference's recursive sibling-adjacent layout
+ *                (merkle_tree.rs:50-58); cap: 2^cap_height digests.
+ * Errors: calls return 0 or a negative P2G_ERR_*; p2g_last_error gives the message.  Conditions on which
+ * the reference panics (inconsistent shapes, cap_height > log2(leaves), size not a power of two) are
+ * P2G_ERR_INVALID -- the Rust shim turns them back into panics.
+ * Threading: a context serialises its calls internally (one stream, one workspace); use one context per
+ * concurrent prover thread.
+ */
+#ifndef P2G_H
+#define P2G_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2G_ABI_VERSION 1
+
+enum { P2G_FIELD_GOLDILOCKS = 0, P2G_FIELD_BABYBEAR = 1 };
+enum { P2G_HASH_POSEIDON_GL12 = 0, P2G_HASH_POSEIDON2_BB16 = 1 };
+enum { P2G_REPR_CANONICAL = 0, P2G_REPR_MONTY_R32 = 1 };
+enum { P2G_INPUT_VALUES = 0, P2G_INPUT_COEFFS = 1 };
+
+enum {
+    P2G_OK = 0,
+    P2G_ERR_INVALID = -1,    /* a shape/argument the reference would panic on */
+    P2G_ERR_NO_DEVICE = -2,  /* no usable CUDA device / context creation failed */
+    P2G_ERR_CUDA = -3,       /* a CUDA runtime call failed */
+    P2G_ERR_OOM = -4,        /* device or pinned-host allocation failed */
+    P2G_ERR_UNSUPPORTED = -5 /* field/hash combination or size outside what the kernels implement */
+};
+
+typedef struct p2g_ctx p2g_ctx;
+
+/* Context: one CUDA device, one stream, resident twiddle / round-constant tables, a reusable workspace.
+ * device_ids/n_devices: the device this context drives (n_devices must be 1; multi-GPU = one context per
+ * device/process, see p2g_commit_desc.shard_*). */
+int32_t p2g_init(const int32_t *device_ids, int32_t n_devices, p2g_ctx **out_ctx);
+void p2g_destroy(p2g_ctx *ctx);
+const char *p2g_last_error(p2g_ctx *ctx); /* ctx may be NULL: last error of p2g_init on this thread */
+int32_t p2g_abi_version(void);
+
+/* Pinned host memory for full-speed PCIe transfers (the Rust shim can back its Vecs with it). */
+void *p2g_host_alloc(p2g_ctx *ctx, size_t bytes);
+void p2g_host_free(p2g_ctx *ctx, void *ptr);
+
+#define P2G_FLAG_DEVICE_INPUT 1u   /* col_ptrs[0] is a DEVICE pointer to the whole column-major [num_cols][n] block */
+#define P2G_FLAG_DEVICE_OUTPUT 2u  /* *_out pointers are DEVICE pointers (coeffs_out[0] = whole block) */
+#define P2G_FLAG_NO_LEAVES_OUT 4u  /* do not return leaves (benchmarks / callers that only need the cap) */
+
+/* One call = one PolynomialBatch::from_values (input_kind VALUES) or from_coeffs (COEFFS). */
+typedef struct {
+    int32_t field;       /* P2G_FIELD_* */
+    int32_t hash;        /* P2G_HASH_*; must match the field */
+    int32_t repr;        /* P2G_REPR_* (BabyBear only; Goldilocks ignores it) */
+    int32_t input_kind;  /* P2G_INPUT_* */
+    uint32_t log_n;      /* degree_log: every column has n = 2^log_n elements */
+    uint32_t num_cols;   /* polynomials in the batch (> 0) */
+    uint32_t rate_bits;
+    uint32_t cap_height;
+    uint32_t num_salt_cols; /* 0, or SALT_SIZE = 4 when `blinding` (oracle.rs:25,134); salts come from the caller
+                               so the RNG stays on the Rust side */
+    uint32_t flags;         /* P2G_FLAG_* */
+    const void *const *col_ptrs;  /* [num_cols] host pointers, n elements each */
+    const void *const *salt_ptrs; /* [num_salt_cols] host pointers, N elements each, natural (un-bit-reversed)
+                                     LDE order exactly like the reference's extra lde_values columns */
+    void *const *coeffs_out; /* [num_cols] host pointers (n each) receiving `polynomials`; may alias col_ptrs;
+                                NULL to skip (from_coeffs callers already own them) */
+    void *leaves_out;        /* [N][leaf_pitch] row-major; NULL with P2G_FLAG_NO_LEAVES_OUT */
+    uint64_t leaf_pitch;     /* elements between rows of leaves_out; 0 = num_cols + num_salt_cols */
+    void *digests_out;       /* 2*(N - 2^cap_height) * 32 bytes; may be NULL */
+    void *cap_out;           /* 2^cap_height * 32 bytes */
+    /* multi-GPU shard (0,0 = whole job).  This context computes LDE cosets [shard_index*2^rate_bits/shard_count,
+     * ...) only: leaves rows [shard_index*N/shard_count, ...), the matching slice of `digests` and, when
+     * 2^cap_height >= shard_count, the matching cap entries; *_out then point at those slices.  When
+     * 2^cap_height < shard_count, cap_out receives the shard's single subtree root and digests_out its
+     * local digests; p2g_merkle_finish_cap combines the gathered roots. */
+    uint32_t shard_index, shard_count;
+    /* device seconds of the reference's four timed! scopes (oracle.rs:76-114):
+     * "IFFT", "FFT + blinding", "transpose LDEs" (fused into the previous one here: always 0), "build Merkle tree" */
+    double stage_seconds[4];
+    double h2d_seconds, d2h_seconds;
+} p2g_commit_desc;
+
+int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *desc);
+
+/* MerkleTree::new alone (merkle_tree.rs:152-181), e.g. for the FRI commit-phase trees (fri/prover.rs:108). */
+typedef struct {
+    int32_t field, hash, repr;
+    uint32_t flags;        /* P2G_FLAG_DEVICE_INPUT / P2G_FLAG_DEVICE_OUTPUT */
+    uint64_t num_leaves;   /* power of two */
+    uint64_t leaf_len;     /* elements per leaf; <= 4 (GL) / 8 (BB) takes the no-hash branch of hash_or_noop */
+    uint64_t leaf_pitch;   /* elements between leaves; 0 = leaf_len */
+    uint32_t cap_height;
+    const void *leaves;    /* [num_leaves][leaf_pitch] */
+    void *digests_out;     /* 2*(num_leaves - 2^cap_height) digests */
+    void *cap_out;         /* 2^cap_height digests */
+    double seconds;
+} p2g_merkle_desc;
+
+int32_t p2g_merkle(p2g_ctx *ctx, p2g_merkle_desc *desc);
+
+/* Finish the top of a sharded tree (multi-GPU job with 2^cap_height < shard_count): `roots` holds the
+ * shard_count subtree roots (32 bytes each, host memory, gathered over NCCL / P2P).  They are the leaves of a
+ * tiny tree of digests; the call returns that tree's 2*(shard_count - 2^cap_height) inner digests in the reference
+ * layout (top_digests_out) and the 2^cap_height cap entries.  Node j of tiny layer t is node j of layer
+ * t + log2(leaves per shard) of the full tree, which is where the caller files it in the full `digests` array.
+ * Runs on the context's GPU. */
+int32_t p2g_merkle_finish_cap(p2g_ctx *ctx, int32_t field, int32_t hash, int32_t repr, const void *roots,
+                              uint32_t shard_count, uint32_t cap_height, void *top_digests_out, void *cap_out);
+
+/* Single permutations / hashes on the GPU (known-answer tests, fixtures). Host pointers.
+ * p2g_permute: `count` states of 12 x u64 (GL) or 16 x u32 (BB), permuted in place. */
+int32_t p2g_permute(p2g_ctx *ctx, int32_t hash, int32_t repr, void *states, uint64_t count);
+
+/* Batched transforms on column-major data (parity tests for the NTT kernels; with P2G_FLAG_DEVICE_INPUT/OUTPUT the
+ * column-sharded inverse transform of a multi-GPU commit):
+ * kind 0: ifft (values -> coeffs, field/src/fft.rs:66-94); kind 1: coset LDE of coeffs with shift g and rate_bits,
+ * output column-major natural order [num_cols][N] like lde_values (oracle.rs:125-150). */
+int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, uint32_t log_n, uint32_t num_cols,
+                      uint32_t rate_bits, uint32_t flags, const void *in, void *out);
+
+/* Device workspace currently held by the context (bytes) and a way to drop it. */
+uint64_t p2g_workspace_bytes(p2g_ctx *ctx);
+void p2g_release_workspace(p2g_ctx *ctx);
+
+/* Raw CUDA stream of the context (cudaStream_t) so callers that own device buffers can order work on it. */
+void *p2g_stream(p2g_ctx *ctx);
+/* Number of kernels the context has launched since creation (bench.py reports it as gpu_launches). */
+uint64_t p2g_kernel_launches(p2g_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

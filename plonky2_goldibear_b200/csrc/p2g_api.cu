@@ -1,0 +1,692 @@
+// C ABI + host orchestration of the commit path (see include/p2g.h for the contract).
+//
+// PolynomialBatch::from_values / from_coeffs (plonky2/src/fri/oracle.rs:68-123) become:
+//   H2D columns -> [iNTT passes] -> coefficients -> per LDE coset: [scale + NTT passes -> leaf rows] ->
+//   leaf sponge -> tree levels -> D2H.   No CPU arithmetic on the data path; the host only builds small
+//   twiddle tables (cached per context) and launches kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/p2g.h"
+#include "p2g_internal.h"
+
+using namespace p2g;
+
+namespace {
+
+thread_local std::string g_init_error;
+
+struct Buffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct FieldInfo {
+    int id;
+    size_t elem;          // bytes per element
+    unsigned two_adicity;
+    uint64_t generator;      // canonical
+    uint64_t two_adic_root;  // canonical, order 2^two_adicity
+    unsigned digest_elems;
+};
+// Goldilocks: generator 7, two_adic_generator(32) = 1753635133440165772; BabyBear: generator 31,
+// two_adic_generator(27) = 0x1a427a41 -- values of the external Plonky3 crates the reference links
+// (call sites field/src/fft.rs:16, fri/oracle.rs:141); see SURVEY.md 8(c) for how each is (un)pinned.
+const FieldInfo kGl = {FIELD_GL, 8, 32, 7ull, 1753635133440165772ull, 4};
+const FieldInfo kBb = {FIELD_BB, 4, 27, 31ull, 0x1a427a41ull, 8};
+
+uint64_t f_mul(const FieldInfo &f, uint64_t a, uint64_t b) {
+    return f.id == FIELD_GL ? GlHost::mul(a, b) : BbHost::mul((u32)a, (u32)b);
+}
+uint64_t f_pow(const FieldInfo &f, uint64_t a, uint64_t e) {
+    return f.id == FIELD_GL ? GlHost::pow(a, e) : BbHost::pow((u32)a, e);
+}
+uint64_t f_inv(const FieldInfo &f, uint64_t a) { return f.id == FIELD_GL ? GlHost::inv(a) : BbHost::inv((u32)a); }
+uint64_t f_internal(const FieldInfo &f, uint64_t a) {
+    return f.id == FIELD_GL ? GlHost::to_internal(a) : BbHost::to_internal((u32)a);
+}
+uint64_t two_adic_generator(const FieldInfo &f, unsigned bits) {
+    uint64_t g = f.two_adic_root;
+    for (unsigned i = bits; i < f.two_adicity; i++) g = f_mul(f, g, g);
+    return g;
+}
+unsigned bitrev(unsigned x, unsigned bits) {
+    unsigned r = 0;
+    for (unsigned i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
+}  // namespace
+
+struct p2g_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8];
+    std::mutex mu;
+    std::string error;
+    uint64_t launches = 0;
+    // workspace (grow-only)
+    Buffer in, coeffs, tmp, leaves, digests, cap, salts, misc;
+    // cached device tables
+    std::map<std::pair<int, uint64_t>, void *> pow_tables;   // (field, base) -> [3][1024]
+    std::map<std::pair<int, uint64_t>, void *> root_tables;  // (field, (inverse<<8)|lp) -> [2^(lp-1)]
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        error = buf;
+        return code;
+    }
+};
+
+namespace {
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return ctx->fail(e_ == cudaErrorMemoryAllocation ? P2G_ERR_OOM : P2G_ERR_CUDA, "%s failed: %s", \
+                             #call, cudaGetErrorString(e_));                                             \
+    } while (0)
+
+int ensure(p2g_ctx *ctx, Buffer &b, size_t bytes) {
+    if (b.bytes >= bytes) return 0;
+    if (b.ptr) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(b.ptr);
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    if (bytes == 0) return 0;
+    cudaError_t e = cudaMalloc(&b.ptr, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(P2G_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.bytes = bytes;
+    return 0;
+}
+
+void store_elem(const FieldInfo &f, void *base, size_t idx, uint64_t internal_value) {
+    if (f.id == FIELD_GL)
+        ((uint64_t *)base)[idx] = internal_value;
+    else
+        ((uint32_t *)base)[idx] = (uint32_t)internal_value;
+}
+
+// [3][1024] table of base^(k * 1024^level), internal representation
+int get_pow_table(p2g_ctx *ctx, const FieldInfo &f, uint64_t base, const void **out) {
+    auto key = std::make_pair(f.id, base);
+    auto it = ctx->pow_tables.find(key);
+    if (it != ctx->pow_tables.end()) {
+        *out = it->second;
+        return 0;
+    }
+    std::vector<unsigned char> host(POW_LEVELS * POW_DIGIT * f.elem);
+    uint64_t step = base;
+    for (int lvl = 0; lvl < POW_LEVELS; lvl++) {
+        uint64_t cur = 1;
+        for (int k = 0; k < POW_DIGIT; k++) {
+            store_elem(f, host.data(), (size_t)lvl * POW_DIGIT + k, f_internal(f, cur));
+            cur = f_mul(f, cur, step);
+        }
+        step = cur;  // base^(1024^(lvl+1))
+    }
+    void *d = nullptr;
+    CK(cudaMalloc(&d, host.size()));
+    CK(cudaMemcpyAsync(d, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->pow_tables[key] = d;
+    *out = d;
+    return 0;
+}
+
+// w^k for k < 2^(lp-1), w the primitive 2^lp-th root (or its inverse)
+int get_root_table(p2g_ctx *ctx, const FieldInfo &f, unsigned lp, bool inverse, const void **out) {
+    auto key = std::make_pair(f.id, ((uint64_t)inverse << 8) | lp);
+    auto it = ctx->root_tables.find(key);
+    if (it != ctx->root_tables.end()) {
+        *out = it->second;
+        return 0;
+    }
+    size_t cnt = lp ? ((size_t)1 << (lp - 1)) : 1;
+    std::vector<unsigned char> host(cnt * f.elem);
+    uint64_t w = two_adic_generator(f, lp);
+    if (inverse) w = f_inv(f, w);
+    uint64_t cur = 1;
+    for (size_t k = 0; k < cnt; k++) {
+        store_elem(f, host.data(), k, f_internal(f, cur));
+        cur = f_mul(f, cur, w);
+    }
+    void *d = nullptr;
+    CK(cudaMalloc(&d, host.size()));
+    CK(cudaMemcpyAsync(d, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->root_tables[key] = d;
+    *out = d;
+    return 0;
+}
+
+unsigned pow_levels_for(unsigned log_range) {
+    return log_range <= POW_DIGIT_LOG ? 1 : (log_range <= 2 * POW_DIGIT_LOG ? 2 : 3);
+}
+
+// split log_n into at most three tile sizes, each <= MAX_TILE_LOG, as evenly as possible
+void plan_passes(unsigned log_n, unsigned lps[3], unsigned *num) {
+    unsigned P = log_n <= MAX_TILE_LOG ? 1 : (log_n <= 2 * MAX_TILE_LOG ? 2 : 3);
+    unsigned rem = log_n;
+    for (unsigned i = 0; i < P; i++) {
+        unsigned take = (rem + (P - i) - 1) / (P - i);
+        lps[i] = take;
+        rem -= take;
+    }
+    for (unsigned i = P; i < 3; i++) lps[i] = 0;
+    *num = P;
+}
+
+// Runs one size-2^log_n transform over `num_cols` columns.
+//   inverse: values -> coefficients (natural order, scaled by 1/n), result in `dst` (column-major, user repr)
+//   forward: coset LDE block: coefficients (user repr, `src`) scaled by powers of `shift`, rows written to the
+//            leaf matrix `dst` starting at row_base.
+// `src` is overwritten when inverse (the strided passes run in place); forward uses `tmp` for the strided passes.
+int run_transform(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsigned log_n, unsigned num_cols,
+                  void *src, void *tmp, void *dst, uint64_t dst_stride, uint64_t shift, uint64_t row_base) {
+    unsigned lps[3], P;
+    plan_passes(log_n, lps, &P);
+    const uint64_t n = (uint64_t)1 << log_n;
+    const void *scale = nullptr;
+    unsigned scale_levels = 0;
+    if (!inverse) {
+        int rc = get_pow_table(ctx, f, shift, &scale);
+        if (rc) return rc;
+        scale_levels = pow_levels_for(log_n);
+    }
+    unsigned log_min = log_n;
+    const void *cur_src = src;
+    void *stage_buf = inverse ? src : tmp;
+    for (unsigned i = 0; i < P; i++) {
+        NttPass p;
+        memset(&p, 0, sizeof p);
+        p.num_cols = num_cols;
+        p.log_n = log_n;
+        p.log_min = log_min;
+        p.log_np = lps[i];
+        int rc = get_root_table(ctx, f, lps[i], inverse, &p.roots);
+        if (rc) return rc;
+        p.src = cur_src;
+        p.src_col_stride = n;
+        p.in_user_repr = (i == 0);
+        if (i == 0 && !inverse) {
+            p.scale3 = scale;
+            p.scale_levels = scale_levels;
+        }
+        if (i + 1 < P) {
+            // strided pass with inter-pass twiddles w_{m_in}^(f*j0)
+            uint64_t w = two_adic_generator(f, log_min);
+            if (inverse) w = f_inv(f, w);
+            rc = get_pow_table(ctx, f, w, &p.tw3);
+            if (rc) return rc;
+            p.tw_levels = pow_levels_for(log_min);
+            p.dst = stage_buf;
+            p.dst_col_stride = n;
+            launch_ntt_pass(f.id, repr, NTT_STRIDED, p, ctx->stream, &ctx->launches);
+            cur_src = stage_buf;
+            log_min -= lps[i];
+        } else {
+            p.lp1 = P >= 2 ? lps[0] : 0;
+            p.lp2 = P >= 3 ? lps[1] : 0;
+            p.dst = dst;
+            p.dst_col_stride = dst_stride;
+            p.out_user_repr = 1;
+            if (inverse) {
+                p.use_final_scale = 1;
+                p.final_scale = f_internal(f, f_pow(f, f_inv(f, 2), log_n));  // n^-1 = (1/2)^lg n, fft.rs:78
+                launch_ntt_pass(f.id, repr, NTT_FINAL_NATURAL, p, ctx->stream, &ctx->launches);
+            } else {
+                p.row_base = row_base;
+                launch_ntt_pass(f.id, repr, NTT_FINAL_LEAVES, p, ctx->stream, &ctx->launches);
+            }
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return ctx->fail(P2G_ERR_CUDA, "NTT launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int check_field_hash(p2g_ctx *ctx, int field, int hash, const FieldInfo **out) {
+    if (field == P2G_FIELD_GOLDILOCKS && hash == P2G_HASH_POSEIDON_GL12) {
+        *out = &kGl;
+        return 0;
+    }
+    if (field == P2G_FIELD_BABYBEAR && hash == P2G_HASH_POSEIDON2_BB16) {
+        *out = &kBb;
+        return 0;
+    }
+    return ctx->fail(P2G_ERR_UNSUPPORTED, "unsupported field/hash combination (%d, %d): only Goldilocks+Poseidon(w12) "
+                                         "and BabyBear+Poseidon2(w16) run on the GPU path", field, hash);
+}
+
+unsigned ilog2(uint64_t x) {
+    unsigned l = 0;
+    while (((uint64_t)1 << l) < x) l++;
+    return l;
+}
+
+double ev_seconds(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms * 1e-3;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t p2g_abi_version(void) { return P2G_ABI_VERSION; }
+
+int32_t p2g_init(const int32_t *device_ids, int32_t n_devices, p2g_ctx **out_ctx) {
+    if (!out_ctx) return P2G_ERR_INVALID;
+    *out_ctx = nullptr;
+    if (n_devices != 1 || !device_ids) {
+        g_init_error = "p2g_init: exactly one device per context (use one context per GPU / process)";
+        return P2G_ERR_INVALID;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        g_init_error = std::string("p2g_init: no usable CUDA device (") + cudaGetErrorString(e) +
+                       "); this library has no CPU fallback";
+        return P2G_ERR_NO_DEVICE;
+    }
+    if (device_ids[0] < 0 || device_ids[0] >= count) {
+        g_init_error = "p2g_init: device id out of range";
+        return P2G_ERR_INVALID;
+    }
+    p2g_ctx *ctx = new p2g_ctx();
+    ctx->device = device_ids[0];
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_init_error = std::string("p2g_init: ") + cudaGetErrorString(e);
+        delete ctx;
+        return P2G_ERR_NO_DEVICE;
+    }
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    static PoseidonGlTables gl_tables;
+    static Poseidon2BbTables bb_tables;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        build_poseidon_gl_tables(&gl_tables);
+        build_poseidon2_bb_tables(&bb_tables);
+    });
+    if ((e = upload_hash_tables(&gl_tables, &bb_tables)) != cudaSuccess) {
+        g_init_error = std::string("p2g_init: constant upload failed: ") + cudaGetErrorString(e);
+        delete ctx;
+        return P2G_ERR_CUDA;
+    }
+    *out_ctx = ctx;
+    return P2G_OK;
+}
+
+void p2g_destroy(p2g_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    p2g_release_workspace(ctx);
+    for (auto &kv : ctx->pow_tables) cudaFree(kv.second);
+    for (auto &kv : ctx->root_tables) cudaFree(kv.second);
+    for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *p2g_last_error(p2g_ctx *ctx) { return ctx ? ctx->error.c_str() : g_init_error.c_str(); }
+
+void *p2g_host_alloc(p2g_ctx *ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->fail(P2G_ERR_OOM, "cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void p2g_host_free(p2g_ctx *ctx, void *ptr) {
+    (void)ctx;
+    if (ptr) cudaFreeHost(ptr);
+}
+
+uint64_t p2g_workspace_bytes(p2g_ctx *ctx) {
+    if (!ctx) return 0;
+    return ctx->in.bytes + ctx->coeffs.bytes + ctx->tmp.bytes + ctx->leaves.bytes + ctx->digests.bytes + ctx->cap.bytes +
+           ctx->salts.bytes + ctx->misc.bytes;
+}
+void p2g_release_workspace(p2g_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (Buffer *b : {&ctx->in, &ctx->coeffs, &ctx->tmp, &ctx->leaves, &ctx->digests, &ctx->cap, &ctx->salts, &ctx->misc}) {
+        if (b->ptr) cudaFree(b->ptr);
+        b->ptr = nullptr;
+        b->bytes = 0;
+    }
+}
+void *p2g_stream(p2g_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t p2g_kernel_launches(p2g_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!d) return P2G_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const FieldInfo *fp;
+    int rc = check_field_hash(ctx, d->field, d->hash, &fp);
+    if (rc) return rc;
+    const FieldInfo &f = *fp;
+    const int repr = f.id == FIELD_BB ? d->repr : 0;
+    if (repr != P2G_REPR_CANONICAL && repr != P2G_REPR_MONTY_R32) return ctx->fail(P2G_ERR_INVALID, "bad repr %d", repr);
+    if (d->num_cols == 0) return ctx->fail(P2G_ERR_INVALID, "empty polynomial batch (the reference panics on polynomials[0])");
+    if (d->input_kind != P2G_INPUT_VALUES && d->input_kind != P2G_INPUT_COEFFS) return ctx->fail(P2G_ERR_INVALID, "bad input_kind");
+    const unsigned L = d->log_n, r = d->rate_bits, LN = L + r;
+    if (LN > f.two_adicity) return ctx->fail(P2G_ERR_INVALID, "log_n + rate_bits = %u exceeds the field's two-adicity %u", LN, f.two_adicity);
+    if (LN > 30 || L > 3 * MAX_TILE_LOG) return ctx->fail(P2G_ERR_UNSUPPORTED, "LDE size 2^%u too large for this build", LN);
+    if (d->cap_height > LN) return ctx->fail(P2G_ERR_INVALID, "cap_height=%u should be at most log2(leaves.len())=%u", d->cap_height, LN);
+    if (d->num_salt_cols && !d->salt_ptrs) return ctx->fail(P2G_ERR_INVALID, "salt columns requested without salt_ptrs");
+    if (!d->col_ptrs) return ctx->fail(P2G_ERR_INVALID, "col_ptrs is NULL");
+    unsigned G = d->shard_count ? d->shard_count : 1, gi = d->shard_count ? d->shard_index : 0;
+    if (G & (G - 1)) return ctx->fail(P2G_ERR_INVALID, "shard_count must be a power of two");
+    if (gi >= G) return ctx->fail(P2G_ERR_INVALID, "shard_index out of range");
+    const unsigned lg = ilog2(G);
+    if (lg > r) return ctx->fail(P2G_ERR_UNSUPPORTED, "shard_count %u exceeds the 2^rate_bits = %u cosets", G, 1u << r);
+
+    const uint64_t n = (uint64_t)1 << L, N = (uint64_t)1 << LN;
+    const unsigned c = d->num_cols, salt = d->num_salt_cols, width = c + salt;
+    const unsigned cosets_local = (1u << r) >> lg, coset0 = gi * cosets_local;
+    const uint64_t rows_local = N >> lg, row0 = (uint64_t)gi * rows_local;
+    const unsigned tree_log = LN - lg, cap_local = d->cap_height >= lg ? d->cap_height - lg : 0;
+    const uint64_t num_cap_local = (uint64_t)1 << cap_local;
+    const uint64_t num_digests_local = 2 * (rows_local - num_cap_local);
+    const uint64_t pitch_dev = width;
+    const bool dev_in = d->flags & P2G_FLAG_DEVICE_INPUT, dev_out = d->flags & P2G_FLAG_DEVICE_OUTPUT;
+    const bool want_leaves = !(d->flags & P2G_FLAG_NO_LEAVES_OUT) && d->leaves_out;
+    const uint64_t out_pitch = d->leaf_pitch ? d->leaf_pitch : width;
+    if (out_pitch < width) return ctx->fail(P2G_ERR_INVALID, "leaf_pitch smaller than the leaf length");
+
+    const size_t col_bytes = n * f.elem;
+    cudaStream_t st = ctx->stream;
+    // ---- workspace
+    if (!dev_in || d->input_kind == P2G_INPUT_VALUES) {
+        if ((rc = ensure(ctx, ctx->in, (size_t)c * col_bytes))) return rc;
+    }
+    if (d->input_kind == P2G_INPUT_VALUES)
+        if ((rc = ensure(ctx, ctx->coeffs, (size_t)c * col_bytes))) return rc;
+    if (L > MAX_TILE_LOG)
+        if ((rc = ensure(ctx, ctx->tmp, (size_t)c * col_bytes))) return rc;
+    void *d_leaves = nullptr;
+    if (dev_out && want_leaves && out_pitch == pitch_dev) {
+        d_leaves = d->leaves_out;
+    } else {
+        if ((rc = ensure(ctx, ctx->leaves, (size_t)rows_local * pitch_dev * f.elem))) return rc;
+        d_leaves = ctx->leaves.ptr;
+    }
+    void *d_digests = nullptr, *d_cap = nullptr;
+    if (dev_out && d->digests_out) {
+        d_digests = d->digests_out;
+    } else {
+        if ((rc = ensure(ctx, ctx->digests, std::max<size_t>(32, num_digests_local * 32)))) return rc;
+        d_digests = ctx->digests.ptr;
+    }
+    if (dev_out && d->cap_out) {
+        d_cap = d->cap_out;
+    } else {
+        if ((rc = ensure(ctx, ctx->cap, num_cap_local * 32))) return rc;
+        d_cap = ctx->cap.ptr;
+    }
+
+    // ---- H2D
+    CK(cudaEventRecord(ctx->ev[0], st));
+    void *d_input;
+    if (dev_in) {
+        d_input = const_cast<void *>(d->col_ptrs[0]);
+        if (d->input_kind == P2G_INPUT_VALUES) {
+            // the inverse transform runs in place on its input: work on a copy, the caller keeps its buffer
+            CK(cudaMemcpyAsync(ctx->in.ptr, d_input, (size_t)c * col_bytes, cudaMemcpyDeviceToDevice, st));
+            d_input = ctx->in.ptr;
+        }
+    } else {
+        for (unsigned j = 0; j < c; j++) {
+            if (!d->col_ptrs[j]) return ctx->fail(P2G_ERR_INVALID, "col_ptrs[%u] is NULL", j);
+            CK(cudaMemcpyAsync((char *)ctx->in.ptr + (size_t)j * col_bytes, d->col_ptrs[j], col_bytes, cudaMemcpyHostToDevice, st));
+        }
+        d_input = ctx->in.ptr;
+    }
+    if (salt) {
+        if ((rc = ensure(ctx, ctx->salts, (size_t)salt * N * f.elem))) return rc;
+        for (unsigned j = 0; j < salt; j++)
+            CK(cudaMemcpyAsync((char *)ctx->salts.ptr + (size_t)j * N * f.elem, d->salt_ptrs[j], N * f.elem,
+                               dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+
+    // ---- "IFFT"
+    void *d_coeffs = d_input;
+    if (d->input_kind == P2G_INPUT_VALUES) {
+        void *dst = (dev_out && d->coeffs_out && d->coeffs_out[0]) ? d->coeffs_out[0] : ctx->coeffs.ptr;
+        if ((rc = run_transform(ctx, f, repr, true, L, c, d_input, nullptr, dst, n, 0, 0))) return rc;
+        d_coeffs = dst;
+    }
+    CK(cudaEventRecord(ctx->ev[2], st));
+
+    // ---- "FFT + blinding" + "transpose LDEs": one coset of n rows at a time, written straight into leaf order
+    const uint64_t g = f.generator;
+    const uint64_t wN = two_adic_generator(f, LN);
+    for (unsigned b = 0; b < cosets_local; b++) {
+        unsigned bg = coset0 + b;
+        uint64_t shift = f_mul(f, g, f_pow(f, wN, bitrev(bg, r)));
+        if ((rc = run_transform(ctx, f, repr, false, L, c, d_coeffs, ctx->tmp.ptr, d_leaves, pitch_dev, shift, (uint64_t)b * n)))
+            return rc;
+    }
+    if (salt)
+        launch_salt_scatter(f.id, ctx->salts.ptr, salt, LN, row0, rows_local, d_leaves, pitch_dev, c, st, &ctx->launches);
+    CK(cudaEventRecord(ctx->ev[3], st));
+
+    // ---- "build Merkle tree"
+    TreeShape tree = {tree_log, cap_local, d_digests, d_cap};
+    launch_leaf_hash(f.id, repr, d_leaves, pitch_dev, width, 0, rows_local, tree, st, &ctx->launches);
+    launch_tree_levels(f.id, repr, tree, st, &ctx->launches);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[4], st));
+
+    // ---- D2H
+    if (!dev_out) {
+        if (d->input_kind == P2G_INPUT_VALUES && d->coeffs_out)
+            for (unsigned j = 0; j < c; j++)
+                if (d->coeffs_out[j])
+                    CK(cudaMemcpyAsync(d->coeffs_out[j], (char *)d_coeffs + (size_t)j * col_bytes, col_bytes, cudaMemcpyDeviceToHost, st));
+        if (want_leaves) {
+            if (out_pitch == pitch_dev)
+                CK(cudaMemcpyAsync(d->leaves_out, d_leaves, (size_t)rows_local * pitch_dev * f.elem, cudaMemcpyDeviceToHost, st));
+            else
+                CK(cudaMemcpy2DAsync(d->leaves_out, out_pitch * f.elem, d_leaves, pitch_dev * f.elem, width * f.elem, rows_local,
+                                     cudaMemcpyDeviceToHost, st));
+        }
+        if (d->digests_out && num_digests_local)
+            CK(cudaMemcpyAsync(d->digests_out, d_digests, num_digests_local * 32, cudaMemcpyDeviceToHost, st));
+        if (d->cap_out) CK(cudaMemcpyAsync(d->cap_out, d_cap, num_cap_local * 32, cudaMemcpyDeviceToHost, st));
+    } else if (want_leaves && d_leaves != d->leaves_out) {
+        CK(cudaMemcpy2DAsync(d->leaves_out, out_pitch * f.elem, d_leaves, pitch_dev * f.elem, width * f.elem, rows_local,
+                             cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaEventRecord(ctx->ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    d->h2d_seconds = ev_seconds(ctx->ev[0], ctx->ev[1]);
+    d->stage_seconds[0] = ev_seconds(ctx->ev[1], ctx->ev[2]);
+    d->stage_seconds[1] = ev_seconds(ctx->ev[2], ctx->ev[3]);
+    d->stage_seconds[2] = 0.0;
+    d->stage_seconds[3] = ev_seconds(ctx->ev[3], ctx->ev[4]);
+    d->d2h_seconds = ev_seconds(ctx->ev[4], ctx->ev[5]);
+    return P2G_OK;
+}
+
+static int32_t merkle_locked(p2g_ctx *ctx, p2g_merkle_desc *d) {
+    CK(cudaSetDevice(ctx->device));
+    const FieldInfo *fp;
+    int rc = check_field_hash(ctx, d->field, d->hash, &fp);
+    if (rc) return rc;
+    const FieldInfo &f = *fp;
+    const int repr = f.id == FIELD_BB ? d->repr : 0;
+    if (d->num_leaves == 0 || (d->num_leaves & (d->num_leaves - 1)))
+        return ctx->fail(P2G_ERR_INVALID, "num_leaves must be a power of two (log2_strict)");
+    unsigned lg = ilog2(d->num_leaves);
+    if (d->cap_height > lg) return ctx->fail(P2G_ERR_INVALID, "cap_height=%u should be at most log2(leaves.len())=%u", d->cap_height, lg);
+    if (lg > 31) return ctx->fail(P2G_ERR_UNSUPPORTED, "too many leaves");
+    uint64_t pitch = d->leaf_pitch ? d->leaf_pitch : d->leaf_len;
+    if (pitch < d->leaf_len) return ctx->fail(P2G_ERR_INVALID, "leaf_pitch smaller than leaf_len");
+    if (d->leaf_len > 0xffffffffull) return ctx->fail(P2G_ERR_UNSUPPORTED, "leaf too long");
+    if (!d->leaves && d->leaf_len) return ctx->fail(P2G_ERR_INVALID, "leaves is NULL");
+    const bool dev_in = d->flags & P2G_FLAG_DEVICE_INPUT, dev_out = d->flags & P2G_FLAG_DEVICE_OUTPUT;
+    uint64_t num_cap = (uint64_t)1 << d->cap_height, num_digests = 2 * (d->num_leaves - num_cap);
+    cudaStream_t st = ctx->stream;
+    const void *d_leaves = d->leaves;
+    size_t leaf_bytes = (size_t)d->num_leaves * pitch * f.elem;
+    if (!dev_in) {
+        if ((rc = ensure(ctx, ctx->leaves, std::max<size_t>(leaf_bytes, 32)))) return rc;
+        if (leaf_bytes) CK(cudaMemcpyAsync(ctx->leaves.ptr, d->leaves, leaf_bytes, cudaMemcpyHostToDevice, st));
+        d_leaves = ctx->leaves.ptr;
+    }
+    void *d_dig = d->digests_out, *d_cap = d->cap_out;
+    if (!dev_out) {
+        if ((rc = ensure(ctx, ctx->digests, std::max<size_t>(32, num_digests * 32)))) return rc;
+        if ((rc = ensure(ctx, ctx->cap, num_cap * 32))) return rc;
+        d_dig = ctx->digests.ptr;
+        d_cap = ctx->cap.ptr;
+    }
+    CK(cudaEventRecord(ctx->ev[0], st));
+    TreeShape tree = {lg, d->cap_height, d_dig, d_cap};
+    launch_leaf_hash(f.id, repr, d_leaves, pitch, (uint32_t)d->leaf_len, 0, d->num_leaves, tree, st, &ctx->launches);
+    launch_tree_levels(f.id, repr, tree, st, &ctx->launches);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[1], st));
+    if (!dev_out) {
+        if (d->digests_out && num_digests) CK(cudaMemcpyAsync(d->digests_out, d_dig, num_digests * 32, cudaMemcpyDeviceToHost, st));
+        if (d->cap_out) CK(cudaMemcpyAsync(d->cap_out, d_cap, num_cap * 32, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    d->seconds = ev_seconds(ctx->ev[0], ctx->ev[1]);
+    return P2G_OK;
+}
+
+int32_t p2g_merkle(p2g_ctx *ctx, p2g_merkle_desc *d) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!d) return P2G_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    return merkle_locked(ctx, d);
+}
+
+int32_t p2g_merkle_finish_cap(p2g_ctx *ctx, int32_t field, int32_t hash, int32_t repr, const void *roots,
+                              uint32_t shard_count, uint32_t cap_height, void *top_digests_out, void *cap_out) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const FieldInfo *fp;
+    int rc = check_field_hash(ctx, field, hash, &fp);
+    if (rc) return rc;
+    if (!shard_count || (shard_count & (shard_count - 1))) return ctx->fail(P2G_ERR_INVALID, "shard_count must be a power of two");
+    unsigned lg = ilog2(shard_count);
+    if (cap_height > lg) return ctx->fail(P2G_ERR_INVALID, "cap_height exceeds log2(shard_count)");
+    // The gathered roots are the leaves (already digests: hash_or_noop copies 32-byte leaves) of a tiny tree whose
+    // inner digests, in the reference layout, are exactly the slots that join the shards' local digest blocks.
+    p2g_merkle_desc m;
+    memset(&m, 0, sizeof m);
+    m.field = field;
+    m.hash = hash;
+    m.repr = fp->id == FIELD_BB ? repr : 0;
+    m.num_leaves = shard_count;
+    m.leaf_len = fp->digest_elems;
+    m.cap_height = cap_height;
+    m.leaves = roots;
+    m.digests_out = top_digests_out;
+    m.cap_out = cap_out;
+    return merkle_locked(ctx, &m);
+}
+
+int32_t p2g_permute(p2g_ctx *ctx, int32_t hash, int32_t repr, void *states, uint64_t count) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const FieldInfo &f = hash == P2G_HASH_POSEIDON_GL12 ? kGl : kBb;
+    if (hash != P2G_HASH_POSEIDON_GL12 && hash != P2G_HASH_POSEIDON2_BB16) return ctx->fail(P2G_ERR_UNSUPPORTED, "unknown hash %d", hash);
+    size_t bytes = (size_t)count * (f.id == FIELD_GL ? 12 * 8 : 16 * 4);
+    if (!count) return P2G_OK;
+    int rc = ensure(ctx, ctx->misc, bytes);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->misc.ptr, states, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    launch_permute(f.id, f.id == FIELD_BB ? repr : 0, ctx->misc.ptr, count, ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(states, ctx->misc.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return P2G_OK;
+}
+
+int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, uint32_t log_n, uint32_t num_cols,
+                      uint32_t rate_bits, uint32_t flags, const void *in, void *out) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (field != P2G_FIELD_GOLDILOCKS && field != P2G_FIELD_BABYBEAR) return ctx->fail(P2G_ERR_UNSUPPORTED, "unknown field");
+    const FieldInfo &f = field == P2G_FIELD_GOLDILOCKS ? kGl : kBb;
+    if (f.id == FIELD_GL) repr = 0;
+    if (!num_cols || !in || !out) return ctx->fail(P2G_ERR_INVALID, "empty transform");
+    if (kind == 0) rate_bits = 0;
+    if (log_n + rate_bits > f.two_adicity || log_n + rate_bits > 30 || log_n > 3 * MAX_TILE_LOG) return ctx->fail(P2G_ERR_INVALID, "transform size unsupported");
+    const bool dev_in = flags & P2G_FLAG_DEVICE_INPUT, dev_out = flags & P2G_FLAG_DEVICE_OUTPUT;
+    const uint64_t n = (uint64_t)1 << log_n, N = n << rate_bits;
+    size_t in_bytes = (size_t)num_cols * n * f.elem;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in, in_bytes))) return rc;
+    CK(cudaMemcpyAsync(ctx->in.ptr, in, in_bytes, dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (kind == 0) {
+        void *dst = out;
+        if (!dev_out) {
+            if ((rc = ensure(ctx, ctx->coeffs, in_bytes))) return rc;
+            dst = ctx->coeffs.ptr;
+        }
+        if ((rc = run_transform(ctx, f, repr, true, log_n, num_cols, ctx->in.ptr, nullptr, dst, n, 0, 0))) return rc;
+        if (!dev_out) CK(cudaMemcpyAsync(out, dst, in_bytes, cudaMemcpyDeviceToHost, st));
+    } else if (kind == 1) {
+        size_t out_bytes = (size_t)num_cols * N * f.elem;
+        if ((rc = ensure(ctx, ctx->leaves, out_bytes))) return rc;
+        if ((rc = ensure(ctx, ctx->misc, out_bytes))) return rc;
+        if (log_n > MAX_TILE_LOG)
+            if ((rc = ensure(ctx, ctx->tmp, in_bytes))) return rc;
+        const uint64_t wN = two_adic_generator(f, log_n + rate_bits);
+        for (unsigned b = 0; b < (1u << rate_bits); b++) {
+            uint64_t shift = f_mul(f, f.generator, f_pow(f, wN, bitrev(b, rate_bits)));
+            if ((rc = run_transform(ctx, f, repr, false, log_n, num_cols, ctx->in.ptr, ctx->tmp.ptr, ctx->leaves.ptr, num_cols, shift, (uint64_t)b * n)))
+                return rc;
+        }
+        void *dst = dev_out ? out : ctx->misc.ptr;
+        launch_leaves_to_columns(f.id, ctx->leaves.ptr, num_cols, num_cols, log_n + rate_bits, dst, st, &ctx->launches);
+        CK(cudaGetLastError());
+        if (!dev_out) CK(cudaMemcpyAsync(out, dst, out_bytes, cudaMemcpyDeviceToHost, st));
+    } else {
+        return ctx->fail(P2G_ERR_INVALID, "unknown transform kind %d", kind);
+    }
+    CK(cudaStreamSynchronize(st));
+    return P2G_OK;
+}
+
+}  // extern "C"

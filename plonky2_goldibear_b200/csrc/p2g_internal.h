@@ -1,0 +1,71 @@
+// Internal interfaces between the host orchestration (p2g_api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "field_bb.cuh"
+#include "field_gl.cuh"
+#include "hash_tables.h"
+
+namespace p2g {
+
+enum FieldId { FIELD_GL = 0, FIELD_BB = 1 };
+enum { MAX_TILE_LOG = 10 };  // a CTA transforms at most 2^10 points per column segment in shared memory
+enum { POW_DIGIT_LOG = 10, POW_DIGIT = 1 << POW_DIGIT_LOG, POW_LEVELS = 3 };
+
+// ---- hash.cu -----------------------------------------------------------------------------------
+// Host-side derivation of the Poseidon tables (poseidon_tables.cpp)
+void build_poseidon_gl_tables(PoseidonGlTables *out);
+void build_poseidon2_bb_tables(Poseidon2BbTables *out);
+cudaError_t upload_hash_tables(const PoseidonGlTables *gl, const Poseidon2BbTables *bb);
+
+struct TreeShape {
+    // local tree: num_leaves = 2^log_leaves, 2^cap_height cap entries, subtrees of 2^(log_leaves-cap_height) leaves
+    uint32_t log_leaves;
+    uint32_t cap_height;
+    void *digests;  // 2*(2^log_leaves - 2^cap_height) digests of 32 bytes
+    void *cap;      // 2^cap_height digests
+};
+
+// leaf digests (hash_or_noop of each row) for rows [row_begin, row_begin + row_count) of the local tree
+void launch_leaf_hash(int field, int repr, const void *leaves, uint64_t pitch_elems, uint32_t leaf_len,
+                      uint64_t row_begin, uint64_t row_count, const TreeShape &tree, cudaStream_t stream,
+                      uint64_t *launches);
+// all inner levels (two_to_one) up to the cap
+void launch_tree_levels(int field, int repr, const TreeShape &tree, cudaStream_t stream, uint64_t *launches);
+// permutation of `count` states in place (device pointer)
+void launch_permute(int field, int repr, void *states, uint64_t count, cudaStream_t stream, uint64_t *launches);
+
+// ---- ntt.cu ------------------------------------------------------------------------------------
+struct NttPass {
+    const void *src;
+    void *dst;
+    uint64_t src_col_stride;  // elements
+    uint64_t dst_col_stride;  // elements (column-major outputs) or row pitch (leaf output)
+    uint32_t num_cols;
+    uint32_t log_n;        // column length
+    uint32_t log_min;      // chunk length at this level (log_n for the first pass)
+    uint32_t log_np;       // points transformed per tile
+    uint32_t lp1, lp2;     // tile sizes of the earlier passes (digit sizes of the chunk index), 0 if unused
+    const void *roots;     // w_{np}^k, k < np/2 (direction specific), internal representation
+    const void *tw3;       // [3][1024] power table of w_{m_in} (inter-pass twiddles), or null on the final pass
+    uint32_t tw_levels;
+    const void *scale3;    // [3][1024] power table of the coset shift s_b, or null
+    uint32_t scale_levels;
+    uint64_t final_scale;  // internal representation; multiplied into the outputs of a final pass when use_final_scale
+    uint32_t use_final_scale;
+    uint64_t row_base;     // leaf output: first row of this coset
+    uint32_t in_user_repr;   // 1: src is in the caller's representation (load conversion), 0: internal
+    uint32_t out_user_repr;  // 1: dst is in the caller's representation (canonical / chosen repr)
+};
+enum NttKind { NTT_STRIDED = 0, NTT_FINAL_NATURAL = 1, NTT_FINAL_LEAVES = 2 };
+void launch_ntt_pass(int field, int repr, int kind, const NttPass &p, cudaStream_t stream, uint64_t *launches);
+// copies salt columns (column-major natural LDE order) into the leaf matrix: leaves[k][col0 + j] = salt[j][bitrev(k)]
+void launch_salt_scatter(int field, const void *salts, uint32_t num_salt, uint32_t log_N, uint64_t row_begin,
+                         uint64_t row_count, void *leaves, uint64_t pitch, uint32_t col0, cudaStream_t stream,
+                         uint64_t *launches);
+// out[col][i] (natural LDE order) = leaves[bitrev(i)][col]  -- only for p2g_transform(kind 1)
+void launch_leaves_to_columns(int field, const void *leaves, uint64_t pitch, uint32_t num_cols, uint32_t log_N,
+                              void *out, cudaStream_t stream, uint64_t *launches);
+
+}  // namespace p2g

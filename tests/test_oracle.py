@@ -1,0 +1,200 @@
+"""CPU tests: the oracle against every golden vector / known-answer test the reference holds for the commit
+path, and the properties the reference's own unit tests check."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from util import BB_P, GL_P, synthetic_columns
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _hexlist(xs):
+    return [int(x, 16) for x in xs]
+
+
+# ---- Poseidon Goldilocks: 4 literal KATs (poseidon_goldilocks.rs:1169-1190) ---------------------------------
+def test_poseidon_gl_known_answers(oracle):
+    kat = json.load(open(os.path.join(GOLDEN, "poseidon_gl_kat.json")))
+    assert len(kat["vectors"]) == 4
+    for v in kat["vectors"]:
+        inp = np.array(_hexlist(v["input"]), dtype=np.uint64)
+        exp = np.array(_hexlist(v["output"]), dtype=np.uint64)
+        assert (oracle.permute(oracle.GL, inp, naive=True) == exp).all()
+        assert (oracle.permute(oracle.GL, inp, naive=False) == exp).all()
+
+
+# fast partial rounds == naive rounds (poseidon_goldilocks.rs:1195-1198,1226-1239 `consistency`)
+def test_poseidon_gl_fast_equals_naive(oracle):
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        s = rng.integers(0, GL_P, size=12, dtype=np.uint64)
+        assert (oracle.permute(oracle.GL, s, naive=True) == oracle.permute(oracle.GL, s)).all()
+
+
+# ---- bit reversal: literal table + literals (plonky2/src/util/mod.rs:52-56,63-83) ---------------------------
+def test_reverse_bits_golden(oracle):
+    g = json.load(open(os.path.join(GOLDEN, "reverse_bits_256.json")))
+    out = oracle.reverse_index_bits(np.arange(256, dtype=np.uint64))
+    assert out.tolist() == g["table"]
+    lib = oracle.load()
+    for x, bits, exp in g["reverse_bits"]:
+        assert lib.p2o_reverse_bits(x, bits) == exp
+    assert oracle.reverse_index_bits(np.array([10, 20, 30, 40], dtype=np.uint64)).tolist() == [10, 30, 20, 40]
+    for lg in (16, 17):  # in-place round trip at 2^16 / 2^17 (util/mod.rs:127-147)
+        a = np.arange(1 << lg, dtype=np.uint64)
+        assert (oracle.reverse_index_bits(oracle.reverse_index_bits(a)) == a).all()
+
+
+# ---- golden proof: Merkle paths produced by the reference's own from_values / MerkleTree::new ----------------
+def test_golden_proof_merkle_paths(oracle):
+    g = json.load(open(os.path.join(GOLDEN, "gl_proof_merkle_paths.json")))
+    caps = [np.array([_hexlist(h) for h in c], dtype=np.uint64) for c in g["caps"]]
+    assert g["k_is_prefix"][:4] == [1, 7, 49, 343]  # powers of F::generator() -> generator 7
+    assert len(g["paths"]) >= 30
+    seen = set()
+    for p in g["paths"]:
+        leaf = np.array(_hexlist(p["leaf"]), dtype=np.uint64)
+        sib = np.array([_hexlist(h) for h in p["siblings"]], dtype=np.uint64).reshape(-1, 4)
+        assert oracle.verify_merkle_proof_to_cap(oracle.GL, leaf, p["leaf_index"], caps[p["cap_id"]], sib), p["tree"]
+        # a wrong index or a flipped leaf element must fail
+        assert not oracle.verify_merkle_proof_to_cap(oracle.GL, leaf, p["leaf_index"] ^ 1, caps[p["cap_id"]], sib)
+        bad = leaf.copy()
+        bad[0] ^= np.uint64(1)
+        assert not oracle.verify_merkle_proof_to_cap(oracle.GL, bad, p["leaf_index"], caps[p["cap_id"]], sib)
+        seen.add(p["tree"])
+    assert {"constants_sigmas", "wires", "zs_partial_products", "quotient", "fri_layer_0"} <= seen
+
+
+# ---- field constants: consistency of the values that no literal pins ----------------------------
+def test_field_constants(oracle):
+    lib = oracle.load()
+    assert lib.p2o_order(oracle.GL) == GL_P and lib.p2o_order(oracle.BB) == BB_P
+    assert lib.p2o_generator(oracle.GL) == 7 and lib.p2o_generator(oracle.BB) == 31
+    g32 = lib.p2o_two_adic_generator(oracle.GL, 32)
+    assert g32 == 1753635133440165772 == pow(7, (GL_P - 1) >> 32, GL_P)
+    assert pow(g32, 1 << 31, GL_P) == GL_P - 1
+    b27 = lib.p2o_two_adic_generator(oracle.BB, 27)
+    assert b27 == 0x1A427A41 == pow(31, (BB_P - 1) >> 27, BB_P)
+    assert pow(b27, 1 << 26, BB_P) == BB_P - 1
+    for bits in range(1, 20):  # smaller orders by squaring
+        assert lib.p2o_two_adic_generator(oracle.GL, bits) == pow(g32, 1 << (32 - bits), GL_P)
+        assert lib.p2o_two_adic_generator(oracle.BB, bits) == pow(b27, 1 << (27 - bits), BB_P)
+    assert 943718400 * (1 << 32) % BB_P == 1  # the 2^-32 factor of the Poseidon2 internal layer
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        a, b = int(rng.integers(0, GL_P, dtype=np.uint64)), int(rng.integers(0, GL_P, dtype=np.uint64))
+        assert lib.p2o_mul(oracle.GL, a, b) == a * b % GL_P
+    for a, b in [(GL_P - 1, GL_P - 1), (0xFFFFFFFF, 0xFFFFFFFF00000000), (1 << 63, 1 << 63)]:
+        assert lib.p2o_mul(oracle.GL, a, b) == a * b % GL_P
+
+
+# ---- FFT: field/src/fft.rs:219-253 and polynomial/mod.rs:478-516 -------------------------------------------
+def _naive_eval(coeffs, points, p):
+    out = []
+    for x in points:
+        acc = 0
+        for c in reversed(coeffs):
+            acc = (acc * x + int(c)) % p
+        out.append(acc)
+    return out
+
+
+@pytest.mark.parametrize("field,p", [(0, GL_P), (1, BB_P)])
+def test_fft_matches_naive_and_roundtrips(oracle, field, p):
+    lib = oracle.load()
+    degree, padded = 200, 256
+    coeffs = np.array([i * 1337 % 100 for i in range(degree)] + [0] * (padded - degree), dtype=oracle.DTYPE[field])
+    w = lib.p2o_two_adic_generator(field, 8)
+    points = [pow(w, i, p) for i in range(padded)]
+    vals = oracle.fft(field, coeffs)
+    assert vals.tolist() == _naive_eval(coeffs.tolist(), points, p)
+    assert (oracle.ifft(field, vals) == coeffs).all()
+    for r in range(4):  # zero-tail shortcut equals the plain FFT (fft.rs:244-252)
+        tail = np.concatenate([coeffs, np.zeros((padded << r) - padded, dtype=coeffs.dtype)])
+        assert (oracle.fft(field, tail, 0) == oracle.fft(field, tail, r)).all()
+    # coset FFT vs Horner on the coset (polynomial/mod.rs:478-497)
+    shift = lib.p2o_generator(field)
+    cvals = oracle.coset_fft(field, coeffs, shift)
+    assert cvals.tolist() == _naive_eval(coeffs.tolist(), [shift * x % p for x in points], p)
+
+
+# ---- Merkle tree: every leaf proves (merkle_tree.rs:257-304) ------------------------------------------------
+@pytest.mark.parametrize("field", [0, 1])
+@pytest.mark.parametrize("cap_height", [0, 1, 8])
+def test_merkle_every_leaf_proves(oracle, field, cap_height):
+    rng = np.random.default_rng(5)
+    p = oracle.ORDER[field]
+    n = 256
+    leaves = rng.integers(0, p, size=(n, 7), dtype=np.uint64).astype(oracle.DTYPE[field])
+    if field == 1:
+        leaves = rng.integers(0, p, size=(n, 11), dtype=np.uint64).astype(np.uint32)
+    digests, cap = oracle.merkle_tree(field, leaves, cap_height)
+    for i in range(n):
+        sib = oracle.merkle_prove(field, digests, n, cap_height, i)
+        assert oracle.verify_merkle_proof_to_cap(field, leaves[i], i, cap, sib)
+    with pytest.raises(ValueError):  # test_cap_height_too_big
+        oracle.merkle_tree(field, leaves, 9)
+    # threaded splitting of subtrees must not change a byte
+    d1, c1 = oracle.merkle_tree(field, leaves, cap_height, threads=1)
+    d8, c8 = oracle.merkle_tree(field, leaves, cap_height, threads=8)
+    assert (d1 == d8).all() and (c1 == c8).all() and (d1 == digests).all()
+
+
+def test_hash_or_noop_edges(oracle):
+    for field, d in ((0, 4), (1, 8)):
+        dt = oracle.DTYPE[field]
+        short = np.arange(1, d + 1, dtype=dt)
+        assert (oracle.hash_or_noop(field, short) == short).all()  # len == NUM_HASH_OUT_ELTS: no hash
+        assert (oracle.hash_or_noop(field, short[:2]) == np.array([1, 2] + [0] * (d - 2), dtype=dt)).all()
+        assert (oracle.hash_or_noop(field, np.zeros(0, dtype=dt)) == 0).all()
+        longer = np.arange(1, d + 2, dtype=dt)
+        h = oracle.hash_or_noop(field, longer)
+        st = np.zeros(12 if field == 0 else 16, dtype=dt)
+        st[: d + 1] = longer  # one chunk (len <= 8 for GL; 9 > 8 for BB needs two)
+        if field == 0:
+            assert (h == oracle.permute(field, st)[:d]).all()
+        else:
+            st[:] = 0
+            st[:8] = longer[:8]
+            st = oracle.permute(field, st)
+            st[0] = longer[8]  # overwrite mode keeps the tail of the previous state (hashing.rs:107-110)
+            assert (h == oracle.permute(field, st)[:d]).all()
+
+
+# ---- Poseidon2 BabyBear: structure (gates/poseidon2_babybear.rs:957-1004 has no literal vector) -------------
+def test_poseidon2_bb_structure(oracle):
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, BB_P, size=16, dtype=np.uint64).astype(np.uint32)
+    out = oracle.permute(oracle.BB, a)
+    assert (out < BB_P).all() and not (out == a).all()
+    assert (oracle.permute(oracle.BB, a) == out).all()
+    b = a.copy()
+    b[3] = (int(b[3]) + 1) % BB_P
+    assert (oracle.permute(oracle.BB, b) != out).sum() >= 14  # full diffusion
+
+
+# ---- the pipeline: from_values definition checked independently of the FFT code ---------------------------
+@pytest.mark.parametrize("field,p,c", [(0, GL_P, 5), (1, BB_P, 9)])
+def test_commit_definition(oracle, field, p, c):
+    lib = oracle.load()
+    log_n, r, h = 4, 2, 1
+    n, N = 1 << log_n, 1 << (log_n + r)
+    vals = synthetic_columns(p, oracle.DTYPE[field], c, n)
+    res = oracle.commit(field, vals, oracle.VALUES, r, h)
+    wn = lib.p2o_two_adic_generator(field, log_n)
+    wN = lib.p2o_two_adic_generator(field, log_n + r)
+    g = lib.p2o_generator(field)
+    for j in range(c):
+        co = res["coeffs"][j].tolist()
+        assert _naive_eval(co, [pow(wn, i, p) for i in range(n)], p) == vals[j].tolist()  # interpolation
+        for k in range(N):  # row k holds P(g * w_N^bitrev(k)) (oracle.rs:153-158, fri/verifier.rs:198-199)
+            x = g * pow(wN, lib.p2o_reverse_bits(k, log_n + r), p) % p
+            assert int(res["leaves"][k][j]) == _naive_eval(co, [x], p)[0]
+    d2, c2 = oracle.merkle_tree(field, res["leaves"], h)
+    assert (d2 == res["digests"]).all() and (c2 == res["cap"]).all()
+    # from_coeffs on the coefficients gives the same tree
+    res2 = oracle.commit(field, res["coeffs"], oracle.COEFFS, r, h)
+    assert (res2["cap"] == res["cap"]).all() and (res2["leaves"] == res["leaves"]).all()
