@@ -51,7 +51,8 @@ EXPORTS = [
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libp2g_cuda.so")
+    # P2G_LIBRARY lets kernel experiments load an alternative build of the same CUDA library
+    return os.environ.get("P2G_LIBRARY") or os.path.join(_HERE, "libp2g_cuda.so")
 
 
 def load_library() -> ctypes.CDLL:

@@ -70,8 +70,8 @@ leaf_hash_kernel(const typename H::W *__restrict__ leaves, u64 pitch, u32 len, u
                  u32 log_sub, typename H::W *__restrict__ digests, typename H::W *__restrict__ cap) {
     typedef typename H::W W;
     u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= row_count) return;
-    u64 k = row_begin + t;
+    const bool live = t < row_count;  // no early return: the permutation contains CTA barriers
+    u64 k = row_begin + (live ? t : row_count - 1);
     const W *row = leaves + k * pitch;
     W out[H::DIGEST];
     if (len <= (u32)H::DIGEST) {
@@ -82,13 +82,9 @@ leaf_hash_kernel(const typename H::W *__restrict__ leaves, u64 pitch, u32 len, u
         W s[H::WIDTH];
 #pragma unroll
         for (int i = 0; i < H::WIDTH; i++) s[i] = 0;
-        u32 off = 0;
-        for (; off + H::RATE <= len; off += H::RATE) {
-#pragma unroll
-            for (int i = 0; i < H::RATE; i++) s[i] = H::load(row[off + i]);
-            H::permute(s);
-        }
-        if (off < len) {  // partial last chunk overwrites only its own words (hashing.rs:107-110)
+#pragma unroll 1
+        for (u32 off = 0; off < len; off += H::RATE) {
+            // overwrite mode: a partial last chunk replaces only its own words (hashing.rs:107-110)
 #pragma unroll
             for (int i = 0; i < H::RATE; i++)
                 if (off + i < len) s[i] = H::load(row[off + i]);
@@ -97,6 +93,7 @@ leaf_hash_kernel(const typename H::W *__restrict__ leaves, u64 pitch, u32 len, u
 #pragma unroll
         for (int i = 0; i < H::DIGEST; i++) out[i] = H::store(s[i]);
     }
+    if (!live) return;
     W *dst;
     if (log_sub == 0) {
         dst = cap + k * H::DIGEST;  // tree that is all cap (merkle_tree.rs:124-133)
@@ -115,7 +112,8 @@ tree_level_kernel(typename H::W *__restrict__ digests, typename H::W *__restrict
                   u64 num_parents) {
     typedef typename H::W W;
     u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= num_parents) return;
+    const bool live = idx < num_parents;
+    if (!live) idx = num_parents - 1;
     u32 lg_pps = log_sub - layer - 1;  // log2(parents per subtree)
     u64 sub = idx >> lg_pps, j = idx & (((u64)1 << lg_pps) - 1);
     u64 sub_digests = 2 * (((u64)1 << log_sub) - 1);
@@ -127,6 +125,7 @@ tree_level_kernel(typename H::W *__restrict__ digests, typename H::W *__restrict
 #pragma unroll
     for (int i = 2 * H::DIGEST; i < H::WIDTH; i++) s[i] = 0;
     H::permute(s);
+    if (!live) return;
     W out[H::DIGEST];
 #pragma unroll
     for (int i = 0; i < H::DIGEST; i++) out[i] = H::store(s[i]);
@@ -138,11 +137,13 @@ template <class H>
 __global__ void __launch_bounds__(128) permute_kernel(typename H::W *states, u64 count) {
     typedef typename H::W W;
     u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
+    const bool live = t < count;
+    if (!live) t = count - 1;
     W s[H::WIDTH];
 #pragma unroll
     for (int i = 0; i < H::WIDTH; i++) s[i] = H::load(states[t * H::WIDTH + i]);
     H::permute(s);
+    if (!live) return;
 #pragma unroll
     for (int i = 0; i < H::WIDTH; i++) states[t * H::WIDTH + i] = H::store(s[i]);
 }

@@ -94,54 +94,55 @@ struct Acc192 {
     }
 };
 
+// Code-size discipline: the whole permutation is ~28k dynamic instructions, and a warp that strays from its
+// neighbours misses the instruction cache on every line (first ncu capture: 13 of 18 stalled warps per issue were
+// `no_instruction`).  So there is ONE full-round body (used by both halves), ONE partial-round body and ONE
+// pre-matrix row body, each a real loop, and P2G_ROUND_SYNC keeps the warps of a CTA on the same lines.
+#ifndef P2G_ROUND_SYNC
+#define P2G_ROUND_SYNC() __syncthreads()
+#endif
+
 __device__ __forceinline__ void poseidon_gl_permute(u64 s[12]) {
-    // ---- first 4 full rounds (constants of round r+1 folded into the MDS of round r)
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_pgl.rc[0][i]);
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) {
+    for (int half = 0; half < 2; half++) {
+        // ---- 4 full rounds; the constants of the following layer are folded into each MDS (c_pgl.mds_add)
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = pgl_sbox(s[i]);
-        pgl_mds<true>(s, r < 3 ? c_pgl.rc[r + 1] : c_pgl.first_const);
-    }
-    // ---- dense pre-matrix of the partial rounds (mds_partial_layer_init)
-    {
-        u64 t[11];
+        for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_pgl.pre_add[half][i]);
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+            P2G_ROUND_SYNC();
 #pragma unroll
-        for (int i = 0; i < 11; i++) {
-            Acc192 acc;
-            acc.init();
-#pragma unroll
-            for (int j = 0; j < 11; j++) acc.mac(s[j + 1], c_pgl.init[i][j]);
-            t[i] = acc.reduce();
+            for (int i = 0; i < 12; i++) s[i] = pgl_sbox(s[i]);
+            pgl_mds<true>(s, c_pgl.mds_add[half * 4 + r]);
         }
-#pragma unroll
-        for (int i = 0; i < 11; i++) s[i + 1] = t[i];
-    }
-    // ---- 22 partial rounds in sparse-factor form
+        if (half == 0) {
+            // ---- dense pre-matrix of the partial rounds (mds_partial_layer_init), one output row per iteration
+            u64 t[11];
 #pragma unroll 1
-    for (int r = 0; r < 22; r++) {
-        u64 s0 = gl_add_c(pgl_sbox(s[0]), c_pgl.k[r]);
-        Acc192 acc;
-        acc.init();
-        acc.mac(s0, 25);  // M[0][0] = 17 + 8
+            for (int i = 0; i < 11; i++) {
+                Acc192 acc;
+                acc.init();
 #pragma unroll
-        for (int i = 0; i < 11; i++) acc.mac(s[i + 1], c_pgl.row[r][i]);
+                for (int j = 0; j < 11; j++) acc.mac(s[j + 1], c_pgl.init[i][j]);
+                t[i] = acc.reduce();
+            }
 #pragma unroll
-        for (int i = 0; i < 11; i++) s[i + 1] = gl_mul_add(s0, c_pgl.col[r][i], s[i + 1]);
-        s[0] = acc.reduce();
-    }
-    // ---- last 4 full rounds
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_pgl.rc[26][i]);
+            for (int i = 0; i < 11; i++) s[i + 1] = t[i];
+            // ---- 22 partial rounds in sparse-factor form
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) {
+            for (int r = 0; r < 22; r++) {
+                P2G_ROUND_SYNC();
+                u64 s0 = gl_add_c(pgl_sbox(s[0]), c_pgl.k[r]);
+                Acc192 acc;
+                acc.init();
+                acc.mac(s0, 25);  // M[0][0] = 17 + 8
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = pgl_sbox(s[i]);
-        if (r < 3)
-            pgl_mds<true>(s, c_pgl.rc[27 + r]);
-        else
-            pgl_mds<false>(s, nullptr);
+                for (int i = 0; i < 11; i++) acc.mac(s[i + 1], c_pgl.row[r][i]);
+#pragma unroll
+                for (int i = 0; i < 11; i++) s[i + 1] = gl_mul_add(s0, c_pgl.col[r][i], s[i + 1]);
+                s[0] = acc.reduce();
+            }
+        }
     }
 }
 

@@ -105,7 +105,7 @@ class PolynomialBatch:
         d = field.num_hash_out_elts
         alloc = ctx.pinned_empty if pinned_out else (lambda shape, dtype: np.empty(shape, dtype=dtype))
         leaves = alloc((rows, width), field.dtype) if want_leaves else None
-        digests = alloc((2 * (rows - (1 << cap_local)), d), field.dtype)
+        digests = alloc((max(2 * (rows - (1 << cap_local)), 0), d), field.dtype)
         cap = np.empty((1 << cap_local, d), dtype=field.dtype)
         coeffs = None
         if input_kind == INPUT_VALUES:
