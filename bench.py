@@ -1,0 +1,429 @@
+#!/usr/bin/env python3
+"""Benchmark of the commit hot path: PolynomialBatch::from_values (iNTT -> coset LDE -> bit-reversed row-major leaves ->
+Poseidon Merkle tree to the cap), metric rows*cols/s (BASELINE.json).
+
+  python bench.py --gpus 1 --steps K --warmup W            # our CUDA path (default workload: BASELINE config 2)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # coset-sharded over N GPUs
+  python bench.py --impl reference ...                      # the reference algorithm on the host cores (CPU port)
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (inputs already in HBM), `e2e` = the same
+metric through the C-ABI call with pinned HOST buffers (H2D of the inputs and D2H of every output inside the timed
+region).  `roofline` describes the dominant kernel (the leaf sponge); `roofline_ntt` the NTT passes the BASELINE
+target speaks about; `cpu_baseline` the CPU restatement timed on this box's cores on a bounded sample.
+Only the cpu_baseline / --impl reference legs touch oracle/.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "LDE+Merkle commit rows*cols/s"
+UNIT = "rows*cols/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, field_name):
+    """The reference's CPU algorithm (C++ restatement, OpenMP over columns / subtrees like the reference's rayon) on all
+    host cores, on a bounded sample of the workload.  kind = "port": the Rust reference cannot be built (no toolchain)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import p2o
+    from util import synthetic_columns
+    try:
+        p2o.build(native=True)
+        native = True
+    except Exception as e:  # no compiler on the box: fall back to the portable prebuilt library
+        log("native oracle build failed (%s); using the portable build" % e)
+        native = False
+    fid = p2o.GL if field_name == "gl" else p2o.BB
+    order, dtype = p2o.ORDER[fid], p2o.DTYPE[fid]
+    log_n = min(args.log_n, args.cpu_sample_log_n)
+    cores = p2o.load(native).p2o_max_threads()
+    vals = synthetic_columns(order, dtype, args.cols, 1 << log_n)
+    times, stages = [], None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = p2o.commit(fid, vals, p2o.VALUES, args.rate_bits, args.cap_height, threads=cores, want_leaves=True, native=native)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+            stages = res["stage_seconds"]
+        del res
+    t = float(np.mean(times))
+    value = (args.cols << log_n) / t
+    sample = "2^%d x %d of the 2^%d x %d workload per step (rate_bits=%d, cap_height=%d)" % (
+        log_n, args.cols, args.log_n, args.cols, args.rate_bits, args.cap_height)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64" if field_name == "gl" else "u32", "data": "synthetic",
+        "config": workload_config(args, field_name),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "stage_ms": {k: v * 1e3 for k, v in zip(("IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree"), stages)},
+                         "note": "C++ restatement of the reference CPU path (oracle/), g++ -O3 %s -fopenmp; the Rust reference cannot be built here" % ("-march=native" if native else "-march=x86-64-v3")},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, field_name):
+    name = "Goldilocks+Poseidon(w12)" if field_name == "gl" else "BabyBear+Poseidon2(w16)"
+    return {"workload": "synthetic PolynomialBatch::from_values %s 2^%d rows x %d cols, rate_bits=%d, cap_height=%d" % (
+                name, args.log_n, args.cols, args.rate_bits, args.cap_height),
+            "field": field_name, "log_rows": args.log_n, "cols": args.cols, "rate_bits": args.rate_bits,
+            "cap_height": args.cap_height, "parallelism": "coset-sharded x%d" % args.gpus if args.gpus > 1 else "single GPU",
+            "l2": "inputs (%.2f GB) and leaves (%.2f GB) are larger than the 126 MB L2; no flush needed" % (
+                args.cols * (1 << args.log_n) * (8 if field_name == "gl" else 4) / 1e9,
+                args.cols * (8 << args.log_n) * (8 if field_name == "gl" else 4) / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args, field_name):
+    import torch
+    import torch.distributed as dist
+    import plonky2_goldibear_b200 as p2g
+    from plonky2_goldibear_b200 import _lib
+    from util import synthetic_columns
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with one rank per GPU" % args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the commit path has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    F = p2g.GOLDILOCKS if field_name == "gl" else p2g.BABYBEAR
+    tdtype = torch.int64 if field_name == "gl" else torch.int32
+    ctx = p2g.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.lib.p2g_stream(ctx.handle), device=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    L, c, r, h = args.log_n, args.cols, args.rate_bits, args.cap_height
+    n, N = 1 << L, 1 << (L + r)
+    G = world
+    if G & (G - 1) or G > (1 << r):
+        raise SystemExit("--gpus must be a power of two <= 2^rate_bits")
+    lg = G.bit_length() - 1
+    cpr = (c + G - 1) // G                      # columns whose inverse NTT this rank owns
+    col0, col1 = min(rank * cpr, c), min((rank + 1) * cpr, c)
+    rows_local = N // G
+    cap_local = max(h - lg, 0)
+    d_el = F.num_hash_out_elts
+    es = F.elem_bytes
+
+    # ---- synthetic inputs: value[col][row] = SplitMix64(seed ^ (col << 32 | row)) mod p, seed 42
+    my_cols = synthetic_columns(F.order, F.dtype, c, n)[col0:col1]
+    host_in = ctx.pinned_empty((max(col1 - col0, 1), n), F.dtype)
+    host_in[:col1 - col0] = my_cols
+    with torch.cuda.stream(stream):
+        d_vals = torch.zeros((cpr, n), dtype=tdtype, device=dev)
+        d_vals[:col1 - col0].copy_(torch.from_numpy(host_in[:col1 - col0].view(np.int64 if es == 8 else np.int32)))
+        d_coeff_slice = torch.zeros((cpr, n), dtype=tdtype, device=dev)
+        d_coeffs = torch.zeros((G * cpr, n), dtype=tdtype, device=dev) if G > 1 else d_coeff_slice
+        d_leaves = torch.empty((rows_local, c), dtype=tdtype, device=dev)
+        d_digests = torch.empty((max(2 * (rows_local - (1 << cap_local)), 1), d_el), dtype=tdtype, device=dev)
+        d_cap = torch.empty((1 << cap_local, d_el), dtype=tdtype, device=dev)
+    stream.synchronize()
+
+    def make_desc(input_kind, flags):
+        desc = _lib.CommitDesc()
+        desc.field, desc.hash, desc.repr, desc.input_kind = F.field_id, F.hash_id, 0, input_kind
+        desc.log_n, desc.num_cols, desc.rate_bits, desc.cap_height = L, c, r, h
+        desc.flags = flags
+        desc.shard_index, desc.shard_count = (rank, G) if G > 1 else (0, 0)
+        return desc
+
+    keep = []  # keep ctypes arrays alive
+
+    def ptrs(values):
+        arr = (ctypes.c_void_p * len(values))(*values)
+        keep.append(arr)
+        return ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
+
+    # ---- device-resident step
+    dev_desc = make_desc(0 if G == 1 else 1, _lib.FLAG_DEVICE_INPUT | _lib.FLAG_DEVICE_OUTPUT)
+    dev_desc.col_ptrs = ptrs([(d_vals if G == 1 else d_coeffs).data_ptr()])
+    dev_desc.coeffs_out = ptrs([d_coeff_slice.data_ptr()])
+    dev_desc.leaves_out, dev_desc.leaf_pitch = d_leaves.data_ptr(), c
+    dev_desc.digests_out, dev_desc.cap_out = d_digests.data_ptr(), d_cap.data_ptr()
+    kernel_s = np.zeros(4)
+
+    def device_step():
+        if G > 1:
+            # column-sharded inverse NTT, then every rank needs all coefficient columns: one NVLink all-gather
+            ctx.check(ctx.lib.p2g_transform(ctx.handle, F.field_id, 0, 0, L, cpr, 0,
+                                            _lib.FLAG_DEVICE_INPUT | _lib.FLAG_DEVICE_OUTPUT,
+                                            d_vals.data_ptr(), d_coeff_slice.data_ptr()))
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(d_coeffs, d_coeff_slice)
+            stream.synchronize()
+        ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(dev_desc)))
+        kernel_s[:] += np.array(list(dev_desc.kernel_seconds))
+
+    def barrier():
+        if G > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dev_ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if G > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) * 1e-3, float(t[1]) * 1e-3
+
+    for _ in range(args.warmup):
+        device_step()
+    kernel_s[:] = 0
+    launches0 = ctx.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_total, _ = timed(device_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.kernel_launches() - launches0
+    t_step = dev_total / args.steps
+    ksec = kernel_s / args.steps
+    value = (c << L) / t_step
+
+    # parity guard inside the bench: the cap of the timed run must equal the cap of the e2e (host) run below
+    cap_dev = d_cap.cpu().numpy().view(F.dtype).copy()
+
+    # ---- end-to-end step: host (pinned) buffers in, every output back to the host
+    e2e = None
+    if not args.no_e2e:
+        h_coeffs = ctx.pinned_empty((max(col1 - col0, 1), n), F.dtype)
+        h_leaves = ctx.pinned_empty((rows_local, c), F.dtype)
+        h_digests = ctx.pinned_empty((max(2 * (rows_local - (1 << cap_local)), 1), d_el), F.dtype)
+        h_cap = ctx.pinned_empty((1 << cap_local, d_el), F.dtype)
+        if G == 1:
+            e_desc = make_desc(0, 0)
+            e_desc.col_ptrs = ptrs([host_in[j].ctypes.data for j in range(c)])
+            e_desc.coeffs_out = ptrs([h_coeffs[j].ctypes.data for j in range(c)])
+        else:
+            e_desc = make_desc(1, _lib.FLAG_DEVICE_INPUT)  # coefficients arrive over NVLink, outputs go to the host
+            e_desc.col_ptrs = ptrs([d_coeffs.data_ptr()])
+        e_desc.leaves_out, e_desc.leaf_pitch = h_leaves.ctypes.data, c
+        e_desc.digests_out, e_desc.cap_out = h_digests.ctypes.data, h_cap.ctypes.data
+        t_in = torch.from_numpy(host_in[:max(col1 - col0, 1)].view(np.int64 if es == 8 else np.int32))
+        t_hc = torch.from_numpy(h_coeffs.view(np.int64 if es == 8 else np.int32))
+
+        def e2e_step():
+            if G > 1:
+                with torch.cuda.stream(stream):
+                    d_vals[:col1 - col0].copy_(t_in[:col1 - col0], non_blocking=True)       # H2D of this rank's columns
+                ctx.check(ctx.lib.p2g_transform(ctx.handle, F.field_id, 0, 0, L, cpr, 0,
+                                                _lib.FLAG_DEVICE_INPUT | _lib.FLAG_DEVICE_OUTPUT,
+                                                d_vals.data_ptr(), d_coeff_slice.data_ptr()))
+                with torch.cuda.stream(stream):
+                    t_hc[:col1 - col0].copy_(d_coeff_slice[:col1 - col0], non_blocking=True)  # D2H of its coefficients
+                    dist.all_gather_into_tensor(d_coeffs, d_coeff_slice)
+                stream.synchronize()
+            ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(e_desc)))
+
+        e2e_step()
+        assert (h_cap == cap_dev).all(), "device-resident and end-to-end runs disagree on the Merkle cap"
+        _, e2e_wall = timed(e2e_step, args.e2e_steps)
+        te = e2e_wall / args.e2e_steps
+        h2d = (col1 - col0) * n * es
+        d2h = (col1 - col0) * n * es + rows_local * c * es + h_digests.nbytes + h_cap.nbytes
+        tb = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+        if G > 1:
+            dist.all_reduce(tb)
+        e2e = {"value": (c << L) / te, "unit": UNIT, "h2d_bytes_per_step": int(tb[0]), "d2h_bytes_per_step": int(tb[1]),
+               "ms_per_step": te * 1e3, "steps": args.e2e_steps,
+               "note": "p2g_commit with pinned host buffers; all of coeffs, leaves, digests, cap copied back"}
+
+    if rank != 0:
+        if G > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline bookkeeping (algorithmic bytes per kernel)
+    peak, peak_src = measured_peak()
+    leaves_bytes = rows_local * c * es
+    leaf_digest_bytes = rows_local * 32
+    t_leaf = ksec[2]
+    perms = N * ((c + 7) // 8) + (N - (1 << h)) if c > d_el else N - (1 << h)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "leaf_sponge_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("log_rows") == L and tj.get("cols") == c and tj.get("field") == field_name:
+                traffic = tj["dram_bytes_per_launch"] / 1e9
+        except Exception:
+            pass
+    roofline = {"kernel": "leaf_hash_kernel (Poseidon sponge over the leaf rows; integer-pipe bound, see int_pipe)",
+                "bound": "hbm", "achieved": (leaves_bytes + leaf_digest_bytes) / t_leaf / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": (leaves_bytes + leaf_digest_bytes) / t_leaf / 1e9 / peak, "traffic": traffic,
+                "peak_source": peak_src, "ms_per_launch": t_leaf * 1e3,
+                "algorithmic_gb_per_launch": (leaves_bytes + leaf_digest_bytes) / 1e9}
+    ntt_bytes = es * n * c * (2 + (1 << r)) / G
+    t_ntt = ksec[0] + ksec[1]
+    roofline_ntt = {"kernels": "ntt_strided_kernel + ntt_final_natural_kernel + ntt_final_leaves_kernel", "bound": "hbm",
+                    "achieved": ntt_bytes / t_ntt / 1e9, "peak": peak, "unit": "GB/s", "frac": ntt_bytes / t_ntt / 1e9 / peak,
+                    "ms": t_ntt * 1e3, "algorithmic_gb": ntt_bytes / 1e9}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64" if field_name == "gl" else "u32", "data": "synthetic",
+        "config": workload_config(args, field_name), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_ntt": roofline_ntt,
+        "stage_ms": {"inverse_ntt": ksec[0] * 1e3, "lde_ntt": ksec[1] * 1e3, "leaf_sponge": ksec[2] * 1e3, "tree_levels": ksec[3] * 1e3},
+        "hash": {"permutations_per_step": int(perms), "permutations_per_s": perms / G / (ksec[2] + ksec[3])},
+    }
+    if G == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, field_name)
+    print(json.dumps(line), flush=True)
+    if G > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, field_name):
+    """The oracle (kind "port") timed on this box's host cores on a bounded sample of the same workload."""
+    from oracle import p2o
+    from util import synthetic_columns
+    try:
+        p2o.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    fid = p2o.GL if field_name == "gl" else p2o.BB
+    log_n = min(args.log_n, args.cpu_sample_log_n)
+    cores = p2o.load(native).p2o_max_threads()
+    vals = synthetic_columns(p2o.ORDER[fid], p2o.DTYPE[fid], args.cols, 1 << log_n)
+    best, stages = None, None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        res = p2o.commit(fid, vals, p2o.VALUES, args.rate_bits, args.cap_height, threads=cores, native=native)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, stages = dt, res["stage_seconds"]
+        del res
+    return {"value": (args.cols << log_n) / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "2^%d x %d (1/%d of the rows of the workload), best of 2, all %d host threads" % (
+                log_n, args.cols, 1 << (args.log_n - log_n), cores),
+            "ms": best * 1e3,
+            "stage_ms": {k: v * 1e3 for k, v in zip(("IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree"), stages)}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--field", default="gl", choices=["gl", "bb"])
+    ap.add_argument("--log-n", type=int, default=None)
+    ap.add_argument("--cols", type=int, default=None)
+    ap.add_argument("--rate-bits", type=int, default=3)
+    ap.add_argument("--cap-height", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-log-n", type=int, default=16)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("note: timing rules ask for >= 3 warm-up steps; got %d" % args.warmup)
+    if args.log_n is None:
+        args.log_n = 20 if args.field == "gl" else 22
+    if args.cols is None:
+        args.cols = 135 if args.field == "gl" else 256
+    if args.impl == "reference":
+        run_reference(args, args.field)
+    else:
+        run_ours(args, args.field)
+
+
+if __name__ == "__main__":
+    main()

@@ -106,6 +106,9 @@ typedef struct {
      * "IFFT", "FFT + blinding", "transpose LDEs" (fused into the previous one here: always 0), "build Merkle tree" */
     double stage_seconds[4];
     double h2d_seconds, d2h_seconds;
+    /* finer split of the same device time: [0] inverse-NTT passes, [1] LDE NTT passes (+ salt scatter),
+     * [2] leaf sponge kernel, [3] tree-level kernels */
+    double kernel_seconds[4];
 } p2g_commit_desc;
 
 int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *desc);

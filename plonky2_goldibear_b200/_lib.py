@@ -31,6 +31,7 @@ class CommitDesc(ctypes.Structure):
         ("leaf_pitch", ctypes.c_uint64), ("digests_out", ctypes.c_void_p), ("cap_out", ctypes.c_void_p),
         ("shard_index", ctypes.c_uint32), ("shard_count", ctypes.c_uint32),
         ("stage_seconds", ctypes.c_double * 4), ("h2d_seconds", ctypes.c_double), ("d2h_seconds", ctypes.c_double),
+        ("kernel_seconds", ctypes.c_double * 4),
     ]
 
 

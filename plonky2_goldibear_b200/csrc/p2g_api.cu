@@ -505,6 +505,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     // ---- "build Merkle tree"
     TreeShape tree = {tree_log, cap_local, d_digests, d_cap};
     launch_leaf_hash(f.id, repr, d_leaves, pitch_dev, width, 0, rows_local, tree, st, &ctx->launches);
+    CK(cudaEventRecord(ctx->ev[6], st));
     launch_tree_levels(f.id, repr, tree, st, &ctx->launches);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[4], st));
@@ -537,6 +538,10 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     d->stage_seconds[2] = 0.0;
     d->stage_seconds[3] = ev_seconds(ctx->ev[3], ctx->ev[4]);
     d->d2h_seconds = ev_seconds(ctx->ev[4], ctx->ev[5]);
+    d->kernel_seconds[0] = d->stage_seconds[0];
+    d->kernel_seconds[1] = d->stage_seconds[1];
+    d->kernel_seconds[2] = ev_seconds(ctx->ev[3], ctx->ev[6]);
+    d->kernel_seconds[3] = ev_seconds(ctx->ev[6], ctx->ev[4]);
     return P2G_OK;
 }
 

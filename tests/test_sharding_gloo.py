@@ -1,0 +1,88 @@
+"""World-size-2 gloo test (CPU) of the multi-GPU host logic: column-sharded inverse transform, all-gather of the padded
+coefficient shares, coset/row/digest/cap slices per rank.  The arithmetic is done by the oracle here (there is no
+GPU); what is under test is the partition and the exchange that bench.py runs with NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from util import GL_P, synthetic_columns
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, log_n, c, r, h, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle import p2o
+    from plonky2_goldibear_b200.sharding import plan
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 1 << log_n
+    sp = plan(rank, world, c, log_n, r, h)
+    vals = synthetic_columns(GL_P, np.uint64, c, n)
+    # column-sharded inverse transform on this rank's share, zero-padded to cols_per_rank columns
+    share = np.zeros((sp.cols_per_rank, n), dtype=np.uint64)
+    for j in range(sp.col_begin, sp.col_end):
+        share[j - sp.col_begin] = p2o.ifft(p2o.GL, vals[j])
+    gathered = [torch.zeros((sp.cols_per_rank, n), dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(share.view(np.int64)))
+    coeffs = torch.cat(gathered, 0).numpy().view(np.uint64)[:c]
+    # every rank now holds all coefficients; it owns cosets [coset_begin, coset_end) = rows [row_begin, row_end)
+    full = p2o.commit(p2o.GL, coeffs, p2o.COEFFS, r, h)
+    rows = full["leaves"][sp.row_begin:sp.row_end]
+    local_digests, local_cap = p2o.merkle_tree(p2o.GL, rows, sp.local_cap_height)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), coeffs=coeffs, rows=rows, digests=local_digests, cap=local_cap,
+             plan=np.array([sp.row_begin, sp.row_end, sp.digest_begin, sp.digest_end, sp.cap_begin, sp.cap_end,
+                            int(sp.owns_whole_cap_entries)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cap_height", [4, 0])
+def test_two_rank_partition_reassembles(tmp_path, oracle, cap_height):
+    world, log_n, c, r = 2, 6, 7, 3
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, log_n, c, r, cap_height, str(tmp_path)), nprocs=world, join=True)
+    vals = synthetic_columns(GL_P, np.uint64, c, 1 << log_n)
+    ref = oracle.commit(oracle.GL, vals, oracle.VALUES, r, cap_height)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % i)) for i in range(world)]
+    for p in parts:
+        assert (p["coeffs"] == ref["coeffs"]).all()  # the all-gather reassembled every column on every rank
+    assert (np.concatenate([p["rows"] for p in parts]) == ref["leaves"]).all()
+    for p in parts:
+        rb, re_, db, de, cb, ce, whole = [int(x) for x in p["plan"]]
+        assert (ref["digests"][db:de] == p["digests"]).all()  # local digests are a contiguous slice of the global array
+        if whole:
+            assert (ref["cap"][cb:ce] == p["cap"]).all()
+    if cap_height == 0:
+        # 2^cap_height < world: the two shard roots are combined into the single cap entry, and they are the pair of
+        # digests that sits between the two local blocks in the global layout
+        roots = np.concatenate([p["cap"] for p in parts])
+        assert (oracle.two_to_one(oracle.GL, roots[0], roots[1]) == ref["cap"][0]).all()
+        mid = int(parts[0]["plan"][3])
+        assert (ref["digests"][mid:mid + 2] == roots).all()
+
+
+def test_plan_rejects_bad_worlds():
+    from plonky2_goldibear_b200.sharding import plan
+    with pytest.raises(ValueError):
+        plan(0, 3, 135, 20, 3, 4)
+    with pytest.raises(ValueError):
+        plan(0, 16, 135, 20, 3, 4)
+    sp = plan(7, 8, 135, 20, 3, 4)
+    assert (sp.col_begin, sp.col_end, sp.cols_per_rank) == (119, 135, 17)
+    assert (sp.coset_begin, sp.coset_end) == (7, 8) and sp.local_cap_height == 1
+    assert sp.row_end == 1 << 23 and sp.cap_end == 16
