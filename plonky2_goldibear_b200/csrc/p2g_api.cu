@@ -69,7 +69,9 @@ unsigned bitrev(unsigned x, unsigned bits) {
 struct p2g_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H of finished outputs overlaps the hashing kernels
     cudaEvent_t ev[8];
+    cudaEvent_t ready[64];               // "rows of coset b are final" / "coefficients are final" markers
     std::mutex mu;
     std::string error;
     uint64_t launches = 0;
@@ -321,7 +323,9 @@ int32_t p2g_init(const int32_t *device_ids, int32_t n_devices, p2g_ctx **out_ctx
         delete ctx;
         return P2G_ERR_NO_DEVICE;
     }
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto &ev : ctx->ready) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     static PoseidonGlTables gl_tables;
     static Poseidon2BbTables bb_tables;
     static std::once_flag once;
@@ -346,6 +350,8 @@ void p2g_destroy(p2g_ctx *ctx) {
     for (auto &kv : ctx->pow_tables) cudaFree(kv.second);
     for (auto &kv : ctx->root_tables) cudaFree(kv.second);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->ready) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -488,6 +494,16 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         d_coeffs = dst;
     }
     CK(cudaEventRecord(ctx->ev[2], st));
+    cudaStream_t cs = ctx->copy_stream;
+    const bool overlap_d2h = !dev_out;
+    if (overlap_d2h && d->input_kind == P2G_INPUT_VALUES && d->coeffs_out) {
+        // `polynomials` are final now: send them home while the LDE and the hashing run
+        CK(cudaEventRecord(ctx->ready[63], st));
+        CK(cudaStreamWaitEvent(cs, ctx->ready[63], 0));
+        for (unsigned j = 0; j < c; j++)
+            if (d->coeffs_out[j])
+                CK(cudaMemcpyAsync(d->coeffs_out[j], (char *)d_coeffs + (size_t)j * col_bytes, col_bytes, cudaMemcpyDeviceToHost, cs));
+    }
 
     // ---- "FFT + blinding" + "transpose LDEs": one coset of n rows at a time, written straight into leaf order
     const uint64_t g = f.generator;
@@ -497,7 +513,19 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         uint64_t shift = f_mul(f, g, f_pow(f, wN, bitrev(bg, r)));
         if ((rc = run_transform(ctx, f, repr, false, L, c, d_coeffs, ctx->tmp.ptr, d_leaves, pitch_dev, shift, (uint64_t)b * n)))
             return rc;
+        if (overlap_d2h && want_leaves && !salt && b < 62) {
+            // rows [b*n, (b+1)*n) are final (no salt columns to add): start their D2H now
+            CK(cudaEventRecord(ctx->ready[b], st));
+            CK(cudaStreamWaitEvent(cs, ctx->ready[b], 0));
+            char *src = (char *)d_leaves + (size_t)b * n * pitch_dev * f.elem;
+            char *dsth = (char *)d->leaves_out + (size_t)b * n * out_pitch * f.elem;
+            if (out_pitch == pitch_dev)
+                CK(cudaMemcpyAsync(dsth, src, (size_t)n * pitch_dev * f.elem, cudaMemcpyDeviceToHost, cs));
+            else
+                CK(cudaMemcpy2DAsync(dsth, out_pitch * f.elem, src, pitch_dev * f.elem, width * f.elem, n, cudaMemcpyDeviceToHost, cs));
+        }
     }
+    const bool leaves_sent = overlap_d2h && want_leaves && !salt && cosets_local <= 62;
     if (salt)
         launch_salt_scatter(f.id, ctx->salts.ptr, salt, LN, row0, rows_local, d_leaves, pitch_dev, c, st, &ctx->launches);
     CK(cudaEventRecord(ctx->ev[3], st));
@@ -512,11 +540,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
 
     // ---- D2H
     if (!dev_out) {
-        if (d->input_kind == P2G_INPUT_VALUES && d->coeffs_out)
-            for (unsigned j = 0; j < c; j++)
-                if (d->coeffs_out[j])
-                    CK(cudaMemcpyAsync(d->coeffs_out[j], (char *)d_coeffs + (size_t)j * col_bytes, col_bytes, cudaMemcpyDeviceToHost, st));
-        if (want_leaves) {
+        if (want_leaves && !leaves_sent) {
             if (out_pitch == pitch_dev)
                 CK(cudaMemcpyAsync(d->leaves_out, d_leaves, (size_t)rows_local * pitch_dev * f.elem, cudaMemcpyDeviceToHost, st));
             else
@@ -532,6 +556,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     }
     CK(cudaEventRecord(ctx->ev[5], st));
     CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(cs));
     d->h2d_seconds = ev_seconds(ctx->ev[0], ctx->ev[1]);
     d->stage_seconds[0] = ev_seconds(ctx->ev[1], ctx->ev[2]);
     d->stage_seconds[1] = ev_seconds(ctx->ev[2], ctx->ev[3]);

@@ -1,0 +1,40 @@
+#!/usr/bin/env python3
+"""Print the metrics we track from an .ncu-rep (first profiled launch): usage ncu_summary.py file.ncu-rep [launch_idx]"""
+import csv
+import subprocess
+import sys
+
+WANT = [
+    "Kernel Name", "gpu__time_duration.sum", "gpc__cycles_elapsed.avg.per_second", "launch__grid_size", "launch__block_size",
+    "launch__registers_per_thread", "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+]
+STALL = "smsp__average_warps_issue_stalled_"
+
+
+def main():
+    rep = sys.argv[1]
+    idx = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2 + idx]
+    d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    for k in WANT:
+        if k in d:
+            print("%-88s %s %s" % (k, d[k][0], d[k][1]))
+    stalls = sorted(((float(v[0]), k) for k, v in d.items() if k.startswith(STALL) and k.endswith("_per_issue_active.ratio") and v[0]), reverse=True)
+    for v, k in stalls[:8]:
+        print("%-88s %.3f" % (k, v))
+
+
+if __name__ == "__main__":
+    main()
