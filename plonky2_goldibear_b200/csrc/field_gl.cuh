@@ -42,51 +42,61 @@ struct GlHost {  // host-side exact arithmetic used to build tables
 
 __device__ __forceinline__ u64 gl_pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
 
-// (hi:lo) -> any-representative u64.   v = lo + h0*EPS - h1 lies in (-2^32, 2^65); the signed carry word c
-// (-1, 0, +1) says which multiple of 2^64 to fold back in as c*EPS; the folded value always fits in 64 bits.
+// Issue costs measured on B200 (tools/microbench/imad_probe.cu): IMAD.WIDE / IMAD.HI ~3.6 cycles per warp
+// instruction, 32-bit IMAD ~2, IADD3 / LOP3 / SEL / SHF ~1, with no overlap between them.  So the arithmetic below is
+// written to use exactly four IMAD.WIDE per 64x64 product and carry-chain adds for everything else.
+
+// (hi:lo) -> any-representative u64.   v = lo + h0*2^32 - (h0 + h1) lies in (-2^32, 2^65); the signed carry word t
+// (-1, 0, +1) says which multiple of 2^64 to fold back in as t*EPS; the folded value always fits in 64 bits.
 __device__ __forceinline__ u64 gl_reduce128(u64 lo, u64 hi) {
     u32 l0 = (u32)lo, l1 = (u32)(lo >> 32), h0 = (u32)hi, h1 = (u32)(hi >> 32);
-    u32 u0, u1, c;
+    u32 v0, v1, t;
     asm("{\n\t"
-        "mad.lo.cc.u32 %0, %5, 0xffffffff, %3;\n\t"
-        "madc.hi.cc.u32 %1, %5, 0xffffffff, %4;\n\t"
-        "addc.u32 %2, 0, 0;\n\t"
-        "sub.cc.u32 %0, %0, %6;\n\t"
-        "subc.cc.u32 %1, %1, 0;\n\t"
-        "subc.u32 %2, %2, 0;\n\t"
+        ".reg .u32 s0, cs;\n\t"
+        "add.cc.u32 s0, %5, %6;\n\t"     // s = h0 + h1 (33 bits)
+        "addc.u32 cs, 0, 0;\n\t"
+        "sub.cc.u32 %0, %3, s0;\n\t"     // lo - s
+        "subc.cc.u32 %1, %4, cs;\n\t"
+        "subc.u32 %2, 0, 0;\n\t"         // t = -borrow
+        "add.cc.u32 %1, %1, %5;\n\t"     // + h0 * 2^32
+        "addc.u32 %2, %2, 0;\n\t"        // t in {-1, 0, 1}
         "}"
-        : "=&r"(u0), "=&r"(u1), "=&r"(c)
+        : "=&r"(v0), "=&r"(v1), "=&r"(t)
         : "r"(l0), "r"(l1), "r"(h0), "r"(h1));
-    u32 nc = 0u - c;                 // low word of c*EPS
-    u32 sc = (u32)((int)c >> 31);    // high word of c*EPS (sign extension)
+    u32 nt = 0u - t;                // low word of t*EPS
+    u32 st = (u32)((int)t >> 31);   // high word of t*EPS (sign extension)
     asm("{\n\t"
         "add.cc.u32 %0, %0, %2;\n\t"
         "addc.u32 %1, %1, %3;\n\t"
         "}"
-        : "+r"(u0), "+r"(u1)
-        : "r"(nc), "r"(sc));
-    return gl_pack(u0, u1);
+        : "+r"(v0), "+r"(v1)
+        : "r"(nt), "r"(st));
+    return gl_pack(v0, v1);
 }
 
-// full 64x64 -> 128 product; four IMAD.WIDE plus carry glue
+// full 64x64 -> 128 product: four IMAD.WIDE (a0b0, a0b1, a1b0 accumulated onto a0b1 with carry-out, a1b1) joined by
+// 64-bit carry adds.  Written with 64-bit PTX values on purpose: with 32-bit mul.lo/mul.hi pairs ptxas splits a0*b0 into
+// IMAD.HI + IMAD (5.6 issue cycles instead of 3.6) to fold an addend.
 __device__ __forceinline__ void gl_mul128(u64 a, u64 b, u64 &lo, u64 &hi) {
     u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
-    u32 r0, r1, r2, r3;
     asm("{\n\t"
-        "mul.lo.u32 %0,%4,%6;\n\t"
-        "mul.hi.u32 %1,%4,%6;\n\t"
-        "mad.lo.cc.u32 %1,%4,%7,%1;\n\t"
-        "madc.hi.u32 %2,%4,%7,0;\n\t"
-        "mad.lo.cc.u32 %1,%5,%6,%1;\n\t"
-        "madc.hi.cc.u32 %2,%5,%6,%2;\n\t"
-        "addc.u32 %3,0,0;\n\t"
-        "mad.lo.cc.u32 %2,%5,%7,%2;\n\t"
-        "madc.hi.u32 %3,%5,%7,%3;\n\t"
+        ".reg .u64 p0, p3, m, t;\n\t"
+        ".reg .u32 m0, m1, mc, z;\n\t"
+        "mul.wide.u32 p0, %2, %4;\n\t"
+        "mul.wide.u32 m, %2, %5;\n\t"
+        "mov.b64 {m0, m1}, m;\n\t"
+        "mad.lo.cc.u32 m0, %3, %4, m0;\n\t"
+        "madc.hi.cc.u32 m1, %3, %4, m1;\n\t"
+        "addc.u32 mc, 0, 0;\n\t"
+        "mul.wide.u32 p3, %3, %5;\n\t"
+        "mov.u32 z, 0;\n\t"
+        "mov.b64 t, {z, m0};\n\t"
+        "add.cc.u64 %0, p0, t;\n\t"
+        "mov.b64 t, {m1, mc};\n\t"
+        "addc.u64 %1, p3, t;\n\t"
         "}"
-        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "=l"(lo), "=l"(hi)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
-    lo = gl_pack(r0, r1);
-    hi = gl_pack(r2, r3);
 }
 
 __device__ __forceinline__ u64 gl_mul(u64 a, u64 b) {

@@ -24,14 +24,26 @@ __device__ __forceinline__ u64 pgl_sbox(u64 x) {
     return gl_mul(x3, x4);
 }
 
-// acc_lo + acc_hi * 2^32 (both < 2^63) -> representative
+// acc_lo + acc_hi * 2^32 (both < 2^42: sums of twelve 32-bit halves times constants <= 41, plus a constant half)
+// -> representative.  With acc_hi = ah1*2^32 + ah0:  v = acc_lo + ah1*EPS + ah0*2^32  (2^64 = EPS); the first two
+// terms cannot overflow, the last add can carry once, and that carry folds back in as +EPS without a second carry.
 __device__ __forceinline__ u64 pgl_fold(u64 acc_lo, u64 acc_hi) {
-    u64 x = acc_lo + (acc_hi << 32);
-    u32 top = (u32)(acc_hi >> 32) + (u32)(x < acc_lo);  // multiples of 2^64
-    u64 t = (u64)top * 0xffffffffu;
-    u64 r = x + t;
-    if (r < t) r += P2G_GL_EPS;
-    return r;
+    u32 al0 = (u32)acc_lo, al1 = (u32)(acc_lo >> 32), ah0 = (u32)acc_hi, ah1 = (u32)(acc_hi >> 32);
+    u32 w0, w1;
+    asm("{\n\t"
+        ".reg .u32 c, nc;\n\t"
+        "sub.cc.u32 %0, %2, %5;\n\t"      // acc_lo - ah1 ...
+        "subc.u32 %1, %3, 0;\n\t"
+        "add.u32 %1, %1, %5;\n\t"         // ... + ah1 * 2^32   (acc_lo + ah1*EPS, < 2^43)
+        "add.cc.u32 %1, %1, %4;\n\t"      // + ah0 * 2^32
+        "addc.u32 c, 0, 0;\n\t"
+        "sub.u32 nc, 0, c;\n\t"           // carry * EPS = (0 : -carry)
+        "add.cc.u32 %0, %0, nc;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(w0), "=&r"(w1)
+        : "r"(al0), "r"(al1), "r"(ah0), "r"(ah1));
+    return gl_pack(w0, w1);
 }
 
 // out = MDS * s (+ next round constants).  MDS = circ(17,15,41,16,2,28,13,13,39,18,34,20) + diag(8,0,...)
@@ -66,31 +78,62 @@ __device__ __forceinline__ void pgl_mds(u64 s[12], const u64 *next_rc) {
     }
 }
 
-// 192-bit accumulator for sums of 128-bit products
+// Accumulator for sums of up to 2^32 128-bit products, kept per 32-bit column so that every partial product is one
+// IMAD.WIDE with carry-out plus one carry add (no per-product 128-bit assembly):
+//   sum = c0 + c1 * 2^32 + c2 * 2^64,   c0 = sum x0*y0, c1 = sum (x0*y1 + x1*y0), c2 = sum x1*y1, each 96 bits.
 struct Acc192 {
-    u64 a0, a1, a2;
-    __device__ __forceinline__ void init() { a0 = a1 = a2 = 0; }
+    u32 c0l, c0h, c0x, c1l, c1h, c1x, c2l, c2h, c2x;
+    __device__ __forceinline__ void init() { c0l = c0h = c0x = c1l = c1h = c1x = c2l = c2h = c2x = 0; }
     __device__ __forceinline__ void mac(u64 x, u64 y) {
-        u64 lo, hi;
-        gl_mul128(x, y, lo, hi);
-        u32 l0 = (u32)lo, l1 = (u32)(lo >> 32), h0 = (u32)hi, h1 = (u32)(hi >> 32);
-        u32 r0 = (u32)a0, r1 = (u32)(a0 >> 32), r2 = (u32)a1, r3 = (u32)(a1 >> 32), r4 = (u32)a2;
+        u32 x0 = (u32)x, x1 = (u32)(x >> 32), y0 = (u32)y, y1 = (u32)(y >> 32);
         asm("{\n\t"
-            "add.cc.u32 %0,%0,%5;\n\t"
-            "addc.cc.u32 %1,%1,%6;\n\t"
-            "addc.cc.u32 %2,%2,%7;\n\t"
-            "addc.cc.u32 %3,%3,%8;\n\t"
-            "addc.u32 %4,%4,0;\n\t"
+            "mad.lo.cc.u32 %0, %9, %11, %0;\n\t"
+            "madc.hi.cc.u32 %1, %9, %11, %1;\n\t"
+            "addc.u32 %2, %2, 0;\n\t"
+            "mad.lo.cc.u32 %3, %9, %12, %3;\n\t"
+            "madc.hi.cc.u32 %4, %9, %12, %4;\n\t"
+            "addc.u32 %5, %5, 0;\n\t"
+            "mad.lo.cc.u32 %3, %10, %11, %3;\n\t"
+            "madc.hi.cc.u32 %4, %10, %11, %4;\n\t"
+            "addc.u32 %5, %5, 0;\n\t"
+            "mad.lo.cc.u32 %6, %10, %12, %6;\n\t"
+            "madc.hi.cc.u32 %7, %10, %12, %7;\n\t"
+            "addc.u32 %8, %8, 0;\n\t"
             "}"
-            : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4)
-            : "r"(l0), "r"(l1), "r"(h0), "r"(h1));
-        a0 = gl_pack(r0, r1);
-        a1 = gl_pack(r2, r3);
-        a2 = r4;
+            : "+r"(c0l), "+r"(c0h), "+r"(c0x), "+r"(c1l), "+r"(c1h), "+r"(c1x), "+r"(c2l), "+r"(c2h), "+r"(c2x)
+            : "r"(x0), "r"(x1), "r"(y0), "r"(y1));
+    }
+    // x * small (y < 2^32): only the two low columns
+    __device__ __forceinline__ void mac_small(u64 x, u32 y) {
+        u32 x0 = (u32)x, x1 = (u32)(x >> 32);
+        asm("{\n\t"
+            "mad.lo.cc.u32 %0, %6, %8, %0;\n\t"
+            "madc.hi.cc.u32 %1, %6, %8, %1;\n\t"
+            "addc.u32 %2, %2, 0;\n\t"
+            "mad.lo.cc.u32 %3, %7, %8, %3;\n\t"
+            "madc.hi.cc.u32 %4, %7, %8, %4;\n\t"
+            "addc.u32 %5, %5, 0;\n\t"
+            "}"
+            : "+r"(c0l), "+r"(c0h), "+r"(c0x), "+r"(c1l), "+r"(c1h), "+r"(c1x)
+            : "r"(x0), "r"(x1), "r"(y));
     }
     __device__ __forceinline__ u64 reduce() const {
-        u64 mid = gl_reduce128(a1, a2);  // (a2:a1) * 2^64 part
-        return gl_reduce128(a0, mid);
+        // limbs t0..t4 of the 160-bit sum
+        u32 t0, t1, t2, t3, t4;
+        asm("{\n\t"
+            "add.cc.u32 %1, %6, %8;\n\t"       // t1 = c0h + c1l
+            "addc.cc.u32 %2, %7, %9;\n\t"      // t2 = c0x + c1h
+            "addc.cc.u32 %3, %10, 0;\n\t"      // t3 = c1x
+            "addc.u32 %4, 0, 0;\n\t"
+            "add.cc.u32 %2, %2, %11;\n\t"      // + c2l
+            "addc.cc.u32 %3, %3, %12;\n\t"     // + c2h
+            "addc.u32 %4, %4, %13;\n\t"        // + c2x
+            "mov.u32 %0, %5;\n\t"
+            "}"
+            : "=&r"(t0), "=&r"(t1), "=&r"(t2), "=&r"(t3), "=&r"(t4)
+            : "r"(c0l), "r"(c0h), "r"(c0x), "r"(c1l), "r"(c1h), "r"(c1x), "r"(c2l), "r"(c2h), "r"(c2x));
+        u64 mid = gl_reduce128(gl_pack(t2, t3), (u64)t4);  // (t4:t3:t2) * 2^64 part
+        return gl_reduce128(gl_pack(t0, t1), mid);
     }
 };
 
@@ -135,7 +178,7 @@ __device__ __forceinline__ void poseidon_gl_permute(u64 s[12]) {
                 u64 s0 = gl_add_c(pgl_sbox(s[0]), c_pgl.k[r]);
                 Acc192 acc;
                 acc.init();
-                acc.mac(s0, 25);  // M[0][0] = 17 + 8
+                acc.mac_small(s0, 25u);  // M[0][0] = 17 + 8
 #pragma unroll
                 for (int i = 0; i < 11; i++) acc.mac(s[i + 1], c_pgl.row[r][i]);
 #pragma unroll
