@@ -164,6 +164,11 @@ def run_ours(args, field_name):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: park the real stdout and send everything else (NCCL's version banner,
+    # library chatter) to stderr until the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus %d needs torchrun with one rank per GPU" % args.gpus)
@@ -364,7 +369,8 @@ def run_ours(args, field_name):
     }
     if G == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, field_name)
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if G > 1:
         dist.destroy_process_group()
 

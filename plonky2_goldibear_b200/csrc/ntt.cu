@@ -54,34 +54,74 @@ __device__ __forceinline__ typename F::E pow3(const typename F::E *__restrict__ 
     return r;
 }
 
-// radix-2 decimation-in-frequency stages over `ncopies` interleaved transforms of np points held in shared memory.
+// Decimation-in-frequency butterflies over 2^lw interleaved transforms of np = 2^lp points held in shared memory,
+// register blocked: a thread takes the 2^K points that differ in the K position bits of a round, runs K stages on
+// them in registers and puts them back, so shared memory is touched once per round (<= 4 stages) and the CTA
+// synchronises once per round instead of once per stage.
 // element (i, w) lives at x[i * si + w * sw]; after the call frequency f sits at i = bitrev_lp(f).
 // W_FAST selects which index varies fastest across threads (w for the strided tiles, i for the contiguous ones).
+template <class F, int K, bool W_FAST>
+__device__ __forceinline__ void dif_round(typename F::E *x, const typename F::E *roots, u32 lp, u32 lw, u32 si, u32 sw,
+                                          u32 s0) {
+    typedef typename F::E E;
+    constexpr u32 R = 1u << K;
+    const u32 lowbits = lp - s0 - K;           // position bits below the round's K bits
+    const u32 units = 1u << (lp - K + lw);     // (hi, low, w) combinations
+    for (u32 u = threadIdx.x; u < units; u += blockDim.x) {
+        u32 w, t;
+        if (W_FAST) {
+            w = u & ((1u << lw) - 1);
+            t = u >> lw;
+        } else {
+            t = u & ((1u << (lp - K)) - 1);
+            w = u >> (lp - K);
+        }
+        const u32 low = t & ((1u << lowbits) - 1);
+        const u32 hi = t >> lowbits;
+        const u32 p0 = (hi << (lp - s0)) | low;
+        E *base = x + p0 * si + w * sw;
+        const u32 stride = si << lowbits;
+        E v[R];
+#pragma unroll
+        for (u32 j = 0; j < R; j++) v[j] = base[j * stride];
+#pragma unroll
+        for (int q = 0; q < K; q++) {
+            const u32 hj = R >> (q + 1);  // distance between butterfly partners, in j
+            const u32 s = s0 + q;
+#pragma unroll
+            for (u32 j = 0; j < R; j++) {
+                if (j & hj) continue;
+                // twiddle w_{np}^{(position mod half) << s}, position = (j mod hj) << lowbits | low
+                const u32 e = (((j & (hj - 1)) << lowbits) | low) << s;
+                E a = v[j], b = v[j + hj];
+                v[j] = F::add(a, b);
+                v[j + hj] = F::mul(F::sub(a, b), roots[e]);
+            }
+        }
+#pragma unroll
+        for (u32 j = 0; j < R; j++) base[j * stride] = v[j];
+    }
+    __syncthreads();
+}
+
 template <class F, bool W_FAST>
 __device__ __forceinline__ void dif_stages(typename F::E *x, const typename F::E *roots, u32 lp, u32 lw, u32 si, u32 sw) {
-    typedef typename F::E E;
-    const u32 np = 1u << lp, nw = 1u << lw;
-    const u32 total = (np >> 1) << lw;
-    for (u32 s = 0; s < lp; s++) {
-        const u32 lh = lp - 1 - s, half = 1u << lh;
-        for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
-            u32 w, b;
-            if (W_FAST) {
-                w = idx & (nw - 1);
-                b = idx >> lw;
-            } else {
-                b = idx & ((np >> 1) - 1);
-                w = idx >> (lp - 1);
-            }
-            u32 pos = b & (half - 1);
-            u32 i0 = ((b >> lh) << (lh + 1)) + pos;
-            E *p0 = x + i0 * si + w * sw;
-            E *p1 = p0 + half * si;
-            E u = *p0, v = *p1;
-            *p0 = F::add(u, v);
-            *p1 = F::mul(F::sub(u, v), roots[pos << s]);
-        }
-        __syncthreads();
+    u32 s0 = 0;
+    // rounds of 4 stages, the remainder split so that no round is a lone stage when it can be avoided
+    while (lp - s0 >= 4 && lp - s0 != 5) {
+        dif_round<F, 4, W_FAST>(x, roots, lp, lw, si, sw, s0);
+        s0 += 4;
+    }
+    u32 rem = lp - s0;
+    if (rem == 5) {
+        dif_round<F, 3, W_FAST>(x, roots, lp, lw, si, sw, s0);
+        dif_round<F, 2, W_FAST>(x, roots, lp, lw, si, sw, s0 + 3);
+    } else if (rem == 3) {
+        dif_round<F, 3, W_FAST>(x, roots, lp, lw, si, sw, s0);
+    } else if (rem == 2) {
+        dif_round<F, 2, W_FAST>(x, roots, lp, lw, si, sw, s0);
+    } else if (rem == 1) {
+        dif_round<F, 1, W_FAST>(x, roots, lp, lw, si, sw, s0);
     }
 }
 

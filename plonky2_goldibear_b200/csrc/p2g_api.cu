@@ -279,6 +279,18 @@ int check_field_hash(p2g_ctx *ctx, int field, int hash, const FieldInfo **out) {
                                          "and BabyBear+Poseidon2(w16) run on the GPU path", field, hash);
 }
 
+// cudaMemcpyAsync from/to pageable memory blocks the calling thread, which would stall the kernel launches behind it:
+// only pinned destinations are copied early on the copy stream.
+bool is_pinned(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 unsigned ilog2(uint64_t x) {
     unsigned l = 0;
     while (((uint64_t)1 << l) < x) l++;
@@ -496,7 +508,10 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     CK(cudaEventRecord(ctx->ev[2], st));
     cudaStream_t cs = ctx->copy_stream;
     const bool overlap_d2h = !dev_out;
-    if (overlap_d2h && d->input_kind == P2G_INPUT_VALUES && d->coeffs_out) {
+    bool coeffs_sent = false;
+    if (overlap_d2h && d->input_kind == P2G_INPUT_VALUES && d->coeffs_out && is_pinned(d->coeffs_out[0]) &&
+        is_pinned(d->coeffs_out[c - 1])) {
+        coeffs_sent = true;
         // `polynomials` are final now: send them home while the LDE and the hashing run
         CK(cudaEventRecord(ctx->ready[63], st));
         CK(cudaStreamWaitEvent(cs, ctx->ready[63], 0));
@@ -508,12 +523,13 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     // ---- "FFT + blinding" + "transpose LDEs": one coset of n rows at a time, written straight into leaf order
     const uint64_t g = f.generator;
     const uint64_t wN = two_adic_generator(f, LN);
+    const bool leaves_early = overlap_d2h && want_leaves && !salt && cosets_local <= 62 && is_pinned(d->leaves_out);
     for (unsigned b = 0; b < cosets_local; b++) {
         unsigned bg = coset0 + b;
         uint64_t shift = f_mul(f, g, f_pow(f, wN, bitrev(bg, r)));
         if ((rc = run_transform(ctx, f, repr, false, L, c, d_coeffs, ctx->tmp.ptr, d_leaves, pitch_dev, shift, (uint64_t)b * n)))
             return rc;
-        if (overlap_d2h && want_leaves && !salt && b < 62) {
+        if (leaves_early && b < 62) {
             // rows [b*n, (b+1)*n) are final (no salt columns to add): start their D2H now
             CK(cudaEventRecord(ctx->ready[b], st));
             CK(cudaStreamWaitEvent(cs, ctx->ready[b], 0));
@@ -525,7 +541,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
                 CK(cudaMemcpy2DAsync(dsth, out_pitch * f.elem, src, pitch_dev * f.elem, width * f.elem, n, cudaMemcpyDeviceToHost, cs));
         }
     }
-    const bool leaves_sent = overlap_d2h && want_leaves && !salt && cosets_local <= 62;
+    const bool leaves_sent = leaves_early;
     if (salt)
         launch_salt_scatter(f.id, ctx->salts.ptr, salt, LN, row0, rows_local, d_leaves, pitch_dev, c, st, &ctx->launches);
     CK(cudaEventRecord(ctx->ev[3], st));
@@ -540,6 +556,10 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
 
     // ---- D2H
     if (!dev_out) {
+        if (d->input_kind == P2G_INPUT_VALUES && d->coeffs_out && !coeffs_sent)
+            for (unsigned j = 0; j < c; j++)
+                if (d->coeffs_out[j])
+                    CK(cudaMemcpyAsync(d->coeffs_out[j], (char *)d_coeffs + (size_t)j * col_bytes, col_bytes, cudaMemcpyDeviceToHost, st));
         if (want_leaves && !leaves_sent) {
             if (out_pitch == pitch_dev)
                 CK(cudaMemcpyAsync(d->leaves_out, d_leaves, (size_t)rows_local * pitch_dev * f.elem, cudaMemcpyDeviceToHost, st));
