@@ -18,8 +18,10 @@
 //   * the LDE never builds the zero-padded size-N input: rows [b*n, (b+1)*n) are the size-n transform of the
 //     coefficients scaled by s_b^j, s_b = g * w_N^{bitrev_r(b)}; the scaling is fused into the
 //     first pass' load.
-// Twiddles: in-tile roots live in shared memory; inter-pass twiddles and coset powers come from three-level
-// 1024-entry power tables (w^e = T0[e & 1023] * T1[(e >> 10) & 1023] * T2[e >> 20]) that stay in L1/L2.
+// Twiddles: in-tile roots live in shared memory.  Inter-pass twiddles (with the coset factor s^j0 merged in on the
+// first LDE pass) come from a per-pass table indexed exactly like the store, so they are read in the same 64-byte
+// runs; the remaining coset factor s^(m*i) is one small per-row table.  Both are built once per (field, size, coset)
+// by a kernel from three-level 1024-entry power tables and cached in the context.
 #include "p2g_internal.h"
 
 namespace p2g {
@@ -38,7 +40,7 @@ template <bool MONTY>
 struct NttBb {
     typedef u32 E;
     static const int W_LOG = 4;  // 16 x 4 B = 64-byte runs
-    static const int PAD = 2;
+    static const int PAD = 4;    // keeps every padded row 16-byte aligned for cp.async
     static __device__ __forceinline__ E load_user(E x) { return MONTY ? BbDev::from_monty(x) : BbDev::from_canonical(x); }
     static __device__ __forceinline__ E store_user(E x) { return MONTY ? x : BbDev::to_canonical(x); }
     static __device__ __forceinline__ E mul(E a, E b) { return bb_mul(a, b); }
@@ -46,13 +48,53 @@ struct NttBb {
     static __device__ __forceinline__ E sub(E a, E b) { return bb_sub(a, b); }
 };
 
+// base^e from the three-level power table (table building only)
 template <class F>
-__device__ __forceinline__ typename F::E pow3(const typename F::E *__restrict__ t, u32 levels, u32 e) {
+__device__ __forceinline__ typename F::E pow3(const typename F::E *__restrict__ t, u32 e) {
     typename F::E r = t[e & (POW_DIGIT - 1)];
-    if (levels > 1) r = F::mul(r, t[POW_DIGIT + ((e >> POW_DIGIT_LOG) & (POW_DIGIT - 1))]);
-    if (levels > 2) r = F::mul(r, t[2 * POW_DIGIT + (e >> (2 * POW_DIGIT_LOG))]);
+    if (e >> POW_DIGIT_LOG) r = F::mul(r, t[POW_DIGIT + ((e >> POW_DIGIT_LOG) & (POW_DIGIT - 1))]);
+    if (e >> (2 * POW_DIGIT_LOG)) r = F::mul(r, t[2 * POW_DIGIT + (e >> (2 * POW_DIGIT_LOG))]);
     return r;
 }
+
+template <class F>
+__global__ void build_tw_table_kernel(typename F::E *out, u32 log_min, u32 log_np, const typename F::E *wpow,
+                                      const typename F::E *spow) {
+    u32 pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >> log_min) return;
+    u32 lmo = log_min - log_np;
+    u32 f = pos >> lmo, j0 = pos & ((1u << lmo) - 1);
+    typename F::E v = pow3<F>(wpow, f * j0);
+    if (spow) v = F::mul(v, pow3<F>(spow, j0));
+    out[pos] = v;
+}
+template <class F>
+__global__ void build_scale_table_kernel(typename F::E *out, u32 log_np, u32 log_mout, const typename F::E *spow) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >> log_np) return;
+    out[i] = pow3<F>(spow, i << log_mout);
+}
+
+// 16-byte asynchronous global->shared copies (LDGSTS): the tile load needs no registers and no per-element round trip
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// what the first round does to an element as it picks it up from the staged tile
+template <class F>
+struct LoadFix {
+    const typename F::E *scale;  // per tile row factor (coset scaling), or null
+    bool user_repr;              // staged data is in the caller's representation
+    __device__ __forceinline__ typename F::E operator()(typename F::E v, u32 row) const {
+        if (user_repr) v = F::load_user(v);
+        if (scale) v = F::mul(v, scale[row]);
+        return v;
+    }
+};
 
 // Decimation-in-frequency butterflies over 2^lw interleaved transforms of np = 2^lp points held in shared memory,
 // register blocked: a thread takes the 2^K points that differ in the K position bits of a round, runs K stages on
@@ -60,9 +102,9 @@ __device__ __forceinline__ typename F::E pow3(const typename F::E *__restrict__ 
 // synchronises once per round instead of once per stage.
 // element (i, w) lives at x[i * si + w * sw]; after the call frequency f sits at i = bitrev_lp(f).
 // W_FAST selects which index varies fastest across threads (w for the strided tiles, i for the contiguous ones).
-template <class F, int K, bool W_FAST>
+template <class F, int K, bool W_FAST, bool FIRST>
 __device__ __forceinline__ void dif_round(typename F::E *x, const typename F::E *roots, u32 lp, u32 lw, u32 si, u32 sw,
-                                          u32 s0) {
+                                          u32 s0, const LoadFix<F> &fix) {
     typedef typename F::E E;
     constexpr u32 R = 1u << K;
     const u32 lowbits = lp - s0 - K;           // position bits below the round's K bits
@@ -84,6 +126,10 @@ __device__ __forceinline__ void dif_round(typename F::E *x, const typename F::E 
         E v[R];
 #pragma unroll
         for (u32 j = 0; j < R; j++) v[j] = base[j * stride];
+        if (FIRST) {
+#pragma unroll
+            for (u32 j = 0; j < R; j++) v[j] = fix(v[j], p0 + (j << lowbits));
+        }
 #pragma unroll
         for (int q = 0; q < K; q++) {
             const u32 hj = R >> (q + 1);  // distance between butterfly partners, in j
@@ -105,23 +151,40 @@ __device__ __forceinline__ void dif_round(typename F::E *x, const typename F::E 
 }
 
 template <class F, bool W_FAST>
-__device__ __forceinline__ void dif_stages(typename F::E *x, const typename F::E *roots, u32 lp, u32 lw, u32 si, u32 sw) {
-    u32 s0 = 0;
-    // rounds of 4 stages, the remainder split so that no round is a lone stage when it can be avoided
+__device__ __forceinline__ void dif_stages(typename F::E *x, const typename F::E *roots, u32 lp, u32 lw, u32 si, u32 sw,
+                                           const LoadFix<F> &fix) {
+    // rounds of 4 stages, the remainder split so that no round is a lone stage when it can be avoided;
+    // the first round also applies the load conversion (representation change, coset factor)
+    u32 first = lp >= 4 && lp != 5 ? 4 : (lp == 5 ? 3 : lp);
+    if (first == 4)
+        dif_round<F, 4, W_FAST, true>(x, roots, lp, lw, si, sw, 0, fix);
+    else if (first == 3)
+        dif_round<F, 3, W_FAST, true>(x, roots, lp, lw, si, sw, 0, fix);
+    else if (first == 2)
+        dif_round<F, 2, W_FAST, true>(x, roots, lp, lw, si, sw, 0, fix);
+    else if (first == 1)
+        dif_round<F, 1, W_FAST, true>(x, roots, lp, lw, si, sw, 0, fix);
+    else {
+        // lp == 0: a one-point transform still owes the conversion
+        for (u32 u = threadIdx.x; u < (1u << lw); u += blockDim.x) x[u * sw] = fix(x[u * sw], 0);
+        __syncthreads();
+        return;
+    }
+    u32 s0 = first;
     while (lp - s0 >= 4 && lp - s0 != 5) {
-        dif_round<F, 4, W_FAST>(x, roots, lp, lw, si, sw, s0);
+        dif_round<F, 4, W_FAST, false>(x, roots, lp, lw, si, sw, s0, fix);
         s0 += 4;
     }
     u32 rem = lp - s0;
     if (rem == 5) {
-        dif_round<F, 3, W_FAST>(x, roots, lp, lw, si, sw, s0);
-        dif_round<F, 2, W_FAST>(x, roots, lp, lw, si, sw, s0 + 3);
+        dif_round<F, 3, W_FAST, false>(x, roots, lp, lw, si, sw, s0, fix);
+        dif_round<F, 2, W_FAST, false>(x, roots, lp, lw, si, sw, s0 + 3, fix);
     } else if (rem == 3) {
-        dif_round<F, 3, W_FAST>(x, roots, lp, lw, si, sw, s0);
+        dif_round<F, 3, W_FAST, false>(x, roots, lp, lw, si, sw, s0, fix);
     } else if (rem == 2) {
-        dif_round<F, 2, W_FAST>(x, roots, lp, lw, si, sw, s0);
+        dif_round<F, 2, W_FAST, false>(x, roots, lp, lw, si, sw, s0, fix);
     } else if (rem == 1) {
-        dif_round<F, 1, W_FAST>(x, roots, lp, lw, si, sw, s0);
+        dif_round<F, 1, W_FAST, false>(x, roots, lp, lw, si, sw, s0, fix);
     }
 }
 
@@ -136,7 +199,7 @@ __device__ __forceinline__ u32 natural_to_chunk(u32 d, u32 lp1, u32 lp2) {
 }
 
 template <class F>
-__global__ void __launch_bounds__(256) ntt_strided_kernel(NttPass p) {
+__global__ void __launch_bounds__(256, 3) ntt_strided_kernel(NttPass p) {
     typedef typename F::E E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     E *x = reinterpret_cast<E *>(smem_raw);
@@ -152,32 +215,52 @@ __global__ void __launch_bounds__(256) ntt_strided_kernel(NttPass p) {
     const u32 q = t >> (lmo - lw), jt = t & (tiles_per_chunk - 1);
     const E *src = (const E *)p.src + (size_t)col * p.src_col_stride + ((size_t)q << p.log_min);
     E *dst = (E *)p.dst + (size_t)col * p.dst_col_stride + ((size_t)q << p.log_min);
-    const E *scale = (const E *)p.scale3;
-    const E *tw = (const E *)p.tw3;
+    const E *tw = (const E *)p.tw_table;
     const u32 total = np << lw;
-    for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        u32 w = idx & (W - 1), i = idx >> lw;
-        u32 j = (i << lmo) + (jt << lw) + w;
-        E v = src[j];
-        if (p.in_user_repr) v = F::load_user(v);
-        if (scale) v = F::mul(v, pow3<F>(scale, p.scale_levels, j));
-        x[idx] = v;
+    // stage the raw tile: row i is a run of W consecutive elements at src[(i << lmo) + jt*W]
+    const u32 run_bytes = (u32)sizeof(E) << lw;
+    if (p.async_ok && run_bytes >= 16) {
+        const u32 per_row = run_bytes >> 4;  // 16-byte pieces per row
+        for (u32 c16 = threadIdx.x; c16 < np * per_row; c16 += blockDim.x) {
+            u32 i = c16 / per_row, part = c16 - i * per_row;
+            cp_async16((char *)x + (size_t)i * run_bytes + part * 16,
+                       (const char *)(src + ((size_t)i << lmo) + (jt << lw)) + part * 16);
+        }
+    } else {
+        for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            u32 w = idx & (W - 1), i = idx >> lw;
+            x[idx] = src[((size_t)i << lmo) + (jt << lw) + w];
+        }
     }
     const E *roots = (const E *)p.roots;
     for (u32 k = threadIdx.x; k < (np >> 1); k += blockDim.x) roots_s[k] = roots[k];
+    cp_async_wait_all();
     __syncthreads();
-    dif_stages<F, true>(x, roots_s, lp, lw, W, 1);
-    for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        u32 w = idx & (W - 1), pp = idx >> lw;
-        u32 f = __brev(pp) >> (32 - lp);
-        u32 j0 = (jt << lw) + w;
-        E v = F::mul(x[idx], pow3<F>(tw, p.tw_levels, f * j0));
-        dst[((size_t)f << lmo) + j0] = v;  // internal representation
+    LoadFix<F> fix = {(const E *)p.scale_table, p.in_user_repr != 0};
+    dif_stages<F, true>(x, roots_s, lp, lw, W, 1, fix);
+    // store with the inter-pass factor; the factor table is indexed like the store, read a batch ahead
+    constexpr u32 B = 8;
+    for (u32 idx0 = threadIdx.x; idx0 < total; idx0 += blockDim.x * B) {
+        E t[B];
+        u32 pos[B];
+#pragma unroll
+        for (u32 k = 0; k < B; k++) {
+            u32 idx = idx0 + k * blockDim.x;
+            u32 w = idx & (W - 1), pp = idx >> lw;
+            u32 f = __brev(pp) >> (32 - lp);
+            pos[k] = (f << lmo) + (jt << lw) + w;
+            if (idx < total) t[k] = tw[pos[k]];
+        }
+#pragma unroll
+        for (u32 k = 0; k < B; k++) {
+            u32 idx = idx0 + k * blockDim.x;
+            if (idx < total) dst[pos[k]] = F::mul(x[idx], t[k]);  // internal representation
+        }
     }
 }
 
 template <class F>
-__global__ void __launch_bounds__(256) ntt_final_natural_kernel(NttPass p) {
+__global__ void __launch_bounds__(256, 3) ntt_final_natural_kernel(NttPass p) {
     typedef typename F::E E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     E *x = reinterpret_cast<E *>(smem_raw);
@@ -194,17 +277,27 @@ __global__ void __launch_bounds__(256) ntt_final_natural_kernel(NttPass p) {
     const E *src = (const E *)p.src + (size_t)col * p.src_col_stride;
     E *dst = (E *)p.dst + (size_t)col * p.dst_col_stride;
     const u32 total = np << lw;
-    for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        u32 i = idx & (np - 1), w = idx >> lp;
-        u32 q = natural_to_chunk(d0 + w, p.lp1, p.lp2);
-        E v = src[((size_t)q << lp) + i];
-        if (p.in_user_repr) v = F::load_user(v);
-        x[w * S + i] = v;
+    const u32 chunk_bytes = (u32)sizeof(E) << lp;
+    if (p.async_ok && chunk_bytes >= 16) {
+        const u32 per_chunk = chunk_bytes >> 4;
+        for (u32 c16 = threadIdx.x; c16 < (per_chunk << lw); c16 += blockDim.x) {
+            u32 w = c16 / per_chunk, part = c16 - w * per_chunk;
+            u32 q = natural_to_chunk(d0 + w, p.lp1, p.lp2);
+            cp_async16((char *)(x + (size_t)w * S) + part * 16, (const char *)(src + ((size_t)q << lp)) + part * 16);
+        }
+    } else {
+        for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            u32 i = idx & (np - 1), w = idx >> lp;
+            u32 q = natural_to_chunk(d0 + w, p.lp1, p.lp2);
+            x[w * S + i] = src[((size_t)q << lp) + i];
+        }
     }
     const E *roots = (const E *)p.roots;
     for (u32 k = threadIdx.x; k < (np >> 1); k += blockDim.x) roots_s[k] = roots[k];
+    cp_async_wait_all();
     __syncthreads();
-    dif_stages<F, false>(x, roots_s, lp, lw, 1, S);
+    LoadFix<F> fix = {nullptr, p.in_user_repr != 0};
+    dif_stages<F, false>(x, roots_s, lp, lw, 1, S, fix);
     const E fs = (E)p.final_scale;
     for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
         u32 w = idx & (W - 1), pp = idx >> lw;
@@ -217,7 +310,7 @@ __global__ void __launch_bounds__(256) ntt_final_natural_kernel(NttPass p) {
 }
 
 template <class F>
-__global__ void __launch_bounds__(256) ntt_final_leaves_kernel(NttPass p) {
+__global__ void __launch_bounds__(256, 3) ntt_final_leaves_kernel(NttPass p) {
     typedef typename F::E E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     E *x = reinterpret_cast<E *>(smem_raw);
@@ -232,14 +325,19 @@ __global__ void __launch_bounds__(256) ntt_final_leaves_kernel(NttPass p) {
     const u32 col0 = cg << F::W_LOG;
     const u32 ncols = min(W, p.num_cols - col0);
     const E *src = (const E *)p.src + (size_t)col0 * p.src_col_stride + ((size_t)q << lp);
-    const E *scale = (const E *)p.scale3;
     const u32 total = np * ncols;
-    for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        u32 i = idx & (np - 1), w = idx >> lp;
-        E v = src[(size_t)w * p.src_col_stride + i];
-        if (p.in_user_repr) v = F::load_user(v);
-        if (scale) v = F::mul(v, pow3<F>(scale, p.scale_levels, i));  // single-pass LDE: q == 0
-        x[w * S + i] = v;
+    const u32 chunk_bytes = (u32)sizeof(E) << lp;
+    if (p.async_ok && chunk_bytes >= 16) {
+        const u32 per_chunk = chunk_bytes >> 4;
+        for (u32 c16 = threadIdx.x; c16 < per_chunk * ncols; c16 += blockDim.x) {
+            u32 w = c16 / per_chunk, part = c16 - w * per_chunk;
+            cp_async16((char *)(x + (size_t)w * S) + part * 16, (const char *)(src + (size_t)w * p.src_col_stride) + part * 16);
+        }
+    } else {
+        for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            u32 i = idx & (np - 1), w = idx >> lp;
+            x[w * S + i] = src[(size_t)w * p.src_col_stride + i];
+        }
     }
     // unused column slots of a ragged last tile must still hold defined values for the butterflies
     for (u32 idx = total + threadIdx.x; idx < (np << F::W_LOG); idx += blockDim.x) {
@@ -248,8 +346,10 @@ __global__ void __launch_bounds__(256) ntt_final_leaves_kernel(NttPass p) {
     }
     const E *roots = (const E *)p.roots;
     for (u32 k = threadIdx.x; k < (np >> 1); k += blockDim.x) roots_s[k] = roots[k];
+    cp_async_wait_all();
     __syncthreads();
-    dif_stages<F, false>(x, roots_s, lp, F::W_LOG, 1, S);
+    LoadFix<F> fix = {(const E *)p.scale_table, p.in_user_repr != 0};  // scale: single-pass LDE (q == 0), row = position
+    dif_stages<F, false>(x, roots_s, lp, F::W_LOG, 1, S, fix);
     // frequency f sits at position bitrev(f), and the leaf order wants row offset bitrev(f): rows are positions.
     const u32 dq = chunk_to_natural(q, p.lp1, p.lp2);
     const u32 rq = lc ? (__brev(dq) >> (32 - lc)) : 0;
@@ -335,6 +435,35 @@ void launch_ntt_pass(int field, int repr, int kind, const NttPass &p, cudaStream
         launch_pass_t<NttBb<true>>(kind, p, stream, launches);
     else
         launch_pass_t<NttBb<false>>(kind, p, stream, launches);
+}
+
+template <class F>
+static void build_tables_t(void *out, u32 log_min, u32 log_np, const void *wpow, const void *spow, bool scale_only,
+                           u32 log_mout, cudaStream_t stream) {
+    typedef typename F::E E;
+    if (scale_only) {
+        u32 n = 1u << log_np;
+        build_scale_table_kernel<F><<<(n + 255) / 256, 256, 0, stream>>>((E *)out, log_np, log_mout, (const E *)spow);
+    } else {
+        u32 n = 1u << log_min;
+        build_tw_table_kernel<F><<<(n + 255) / 256, 256, 0, stream>>>((E *)out, log_min, log_np, (const E *)wpow, (const E *)spow);
+    }
+}
+void launch_build_tw_table(int field, void *out, uint32_t log_min, uint32_t log_np, const void *wpow, const void *spow,
+                           cudaStream_t stream, uint64_t *launches) {
+    if (field == FIELD_GL)
+        build_tables_t<NttGl>(out, log_min, log_np, wpow, spow, false, 0, stream);
+    else
+        build_tables_t<NttBb<true>>(out, log_min, log_np, wpow, spow, false, 0, stream);
+    ++*launches;
+}
+void launch_build_scale_table(int field, void *out, uint32_t log_np, uint32_t log_mout, const void *spow,
+                              cudaStream_t stream, uint64_t *launches) {
+    if (field == FIELD_GL)
+        build_tables_t<NttGl>(out, 0, log_np, nullptr, spow, true, log_mout, stream);
+    else
+        build_tables_t<NttBb<true>>(out, 0, log_np, nullptr, spow, true, log_mout, stream);
+    ++*launches;
 }
 
 void launch_salt_scatter(int field, const void *salts, uint32_t num_salt, uint32_t log_N, uint64_t row_begin,

@@ -13,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/p2g.h"
@@ -80,6 +81,9 @@ struct p2g_ctx {
     // cached device tables
     std::map<std::pair<int, uint64_t>, void *> pow_tables;   // (field, base) -> [3][1024]
     std::map<std::pair<int, uint64_t>, void *> root_tables;  // (field, (inverse<<8)|lp) -> [2^(lp-1)]
+    // per-pass factor tables built on the device: (field, kind, log_min, log_np, w base, s base) -> table
+    std::map<std::tuple<int, int, unsigned, unsigned, uint64_t, uint64_t>, void *> pass_tables;
+    size_t pass_table_bytes = 0;
 
     int fail(int code, const char *fmt, ...) {
         char buf[512];
@@ -180,8 +184,38 @@ int get_root_table(p2g_ctx *ctx, const FieldInfo &f, unsigned lp, bool inverse, 
     return 0;
 }
 
-unsigned pow_levels_for(unsigned log_range) {
-    return log_range <= POW_DIGIT_LOG ? 1 : (log_range <= 2 * POW_DIGIT_LOG ? 2 : 3);
+void drop_pass_tables(p2g_ctx *ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->pass_tables) cudaFree(kv.second);
+    ctx->pass_tables.clear();
+    ctx->pass_table_bytes = 0;
+}
+
+// kind 0: tw_table[m_in] = w^(f*j0) (* s^j0 when sbase != 0); kind 1: scale_table[np] = s^(i << log_mout)
+int get_pass_table(p2g_ctx *ctx, const FieldInfo &f, int kind, unsigned log_min, unsigned log_np, uint64_t wbase,
+                   uint64_t sbase, const void **out) {
+    auto key = std::make_tuple(f.id, kind, log_min, log_np, wbase, sbase);
+    auto it = ctx->pass_tables.find(key);
+    if (it != ctx->pass_tables.end()) {
+        *out = it->second;
+        return 0;
+    }
+    size_t bytes = ((size_t)1 << (kind == 0 ? log_min : log_np)) * f.elem;
+    const void *wpow = nullptr, *spow = nullptr;
+    int rc;
+    if (kind == 0 && (rc = get_pow_table(ctx, f, wbase, &wpow))) return rc;
+    if (sbase && (rc = get_pow_table(ctx, f, sbase, &spow))) return rc;
+    void *d = nullptr;
+    CK(cudaMalloc(&d, bytes));
+    if (kind == 0)
+        launch_build_tw_table(f.id, d, log_min, log_np, wpow, spow, ctx->stream, &ctx->launches);
+    else
+        launch_build_scale_table(f.id, d, log_np, log_min - log_np, spow, ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
+    ctx->pass_tables[key] = d;
+    ctx->pass_table_bytes += bytes;
+    *out = d;
+    return 0;
 }
 
 // split log_n into at most three tile sizes, each <= MAX_TILE_LOG, as evenly as possible
@@ -207,13 +241,6 @@ int run_transform(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsi
     unsigned lps[3], P;
     plan_passes(log_n, lps, &P);
     const uint64_t n = (uint64_t)1 << log_n;
-    const void *scale = nullptr;
-    unsigned scale_levels = 0;
-    if (!inverse) {
-        int rc = get_pow_table(ctx, f, shift, &scale);
-        if (rc) return rc;
-        scale_levels = pow_levels_for(log_n);
-    }
     unsigned log_min = log_n;
     const void *cur_src = src;
     void *stage_buf = inverse ? src : tmp;
@@ -228,18 +255,19 @@ int run_transform(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsi
         if (rc) return rc;
         p.src = cur_src;
         p.src_col_stride = n;
+        p.async_ok = ((uintptr_t)cur_src % 16 == 0) && ((n * f.elem) % 16 == 0 || num_cols == 1);
         p.in_user_repr = (i == 0);
         if (i == 0 && !inverse) {
-            p.scale3 = scale;
-            p.scale_levels = scale_levels;
+            // coset factor s^j, j = i*m_out + j0: the row part s^(m_out*i) on load, s^j0 merged into the pass table
+            rc = get_pass_table(ctx, f, 1, log_min, lps[i], 0, shift, &p.scale_table);
+            if (rc) return rc;
         }
         if (i + 1 < P) {
             // strided pass with inter-pass twiddles w_{m_in}^(f*j0)
             uint64_t w = two_adic_generator(f, log_min);
             if (inverse) w = f_inv(f, w);
-            rc = get_pow_table(ctx, f, w, &p.tw3);
+            rc = get_pass_table(ctx, f, 0, log_min, lps[i], w, (i == 0 && !inverse) ? shift : 0, &p.tw_table);
             if (rc) return rc;
-            p.tw_levels = pow_levels_for(log_min);
             p.dst = stage_buf;
             p.dst_col_stride = n;
             launch_ntt_pass(f.id, repr, NTT_STRIDED, p, ctx->stream, &ctx->launches);
@@ -361,6 +389,7 @@ void p2g_destroy(p2g_ctx *ctx) {
     p2g_release_workspace(ctx);
     for (auto &kv : ctx->pow_tables) cudaFree(kv.second);
     for (auto &kv : ctx->root_tables) cudaFree(kv.second);
+    drop_pass_tables(ctx);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->ready) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->copy_stream);
@@ -389,12 +418,13 @@ void p2g_host_free(p2g_ctx *ctx, void *ptr) {
 uint64_t p2g_workspace_bytes(p2g_ctx *ctx) {
     if (!ctx) return 0;
     return ctx->in.bytes + ctx->coeffs.bytes + ctx->tmp.bytes + ctx->leaves.bytes + ctx->digests.bytes + ctx->cap.bytes +
-           ctx->salts.bytes + ctx->misc.bytes;
+           ctx->salts.bytes + ctx->misc.bytes + ctx->pass_table_bytes;
 }
 void p2g_release_workspace(p2g_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    drop_pass_tables(ctx);
     for (Buffer *b : {&ctx->in, &ctx->coeffs, &ctx->tmp, &ctx->leaves, &ctx->digests, &ctx->cap, &ctx->salts, &ctx->misc}) {
         if (b->ptr) cudaFree(b->ptr);
         b->ptr = nullptr;
@@ -409,6 +439,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     if (!d) return P2G_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
+    if (ctx->pass_table_bytes > ((size_t)2 << 30)) drop_pass_tables(ctx);  // bounded cache; tables are rebuilt on demand
     const FieldInfo *fp;
     int rc = check_field_hash(ctx, d->field, d->hash, &fp);
     if (rc) return rc;
@@ -695,6 +726,7 @@ int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, u
     if (!ctx) return P2G_ERR_NO_DEVICE;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
+    if (ctx->pass_table_bytes > ((size_t)2 << 30)) drop_pass_tables(ctx);
     if (field != P2G_FIELD_GOLDILOCKS && field != P2G_FIELD_BABYBEAR) return ctx->fail(P2G_ERR_UNSUPPORTED, "unknown field");
     const FieldInfo &f = field == P2G_FIELD_GOLDILOCKS ? kGl : kBb;
     if (f.id == FIELD_GL) repr = 0;

@@ -48,18 +48,24 @@ struct NttPass {
     uint32_t log_np;       // points transformed per tile
     uint32_t lp1, lp2;     // tile sizes of the earlier passes (digit sizes of the chunk index), 0 if unused
     const void *roots;     // w_{np}^k, k < np/2 (direction specific), internal representation
-    const void *tw3;       // [3][1024] power table of w_{m_in} (inter-pass twiddles), or null on the final pass
-    uint32_t tw_levels;
-    const void *scale3;    // [3][1024] power table of the coset shift s_b, or null
-    uint32_t scale_levels;
+    const void *tw_table;     // strided pass: [m_in] inter-pass factors, entry f*m_out + j0 = w_{m_in}^(f*j0) (* s^j0 on
+                              // the first LDE pass); same index as the store, so it is read in the same 64-byte runs
+    const void *scale_table;  // [np] coset factors s^(m_out * i) applied to tile row i on load, or null
     uint64_t final_scale;  // internal representation; multiplied into the outputs of a final pass when use_final_scale
     uint32_t use_final_scale;
     uint64_t row_base;     // leaf output: first row of this coset
+    uint32_t async_ok;       // src base and column stride are 16-byte aligned: the tile may be staged with cp.async
     uint32_t in_user_repr;   // 1: src is in the caller's representation (load conversion), 0: internal
     uint32_t out_user_repr;  // 1: dst is in the caller's representation (canonical / chosen repr)
 };
 enum NttKind { NTT_STRIDED = 0, NTT_FINAL_NATURAL = 1, NTT_FINAL_LEAVES = 2 };
 void launch_ntt_pass(int field, int repr, int kind, const NttPass &p, cudaStream_t stream, uint64_t *launches);
+// fills tw_table / scale_table entries from three-level power tables ([3][1024], base^(k*1024^level)):
+//   tw_table[f*m_out + j0] = wpow^(f*j0) * (spow ? spow^j0 : 1);   scale_table[i] = spow^(i << log_mout)
+void launch_build_tw_table(int field, void *out, uint32_t log_min, uint32_t log_np, const void *wpow, const void *spow,
+                           cudaStream_t stream, uint64_t *launches);
+void launch_build_scale_table(int field, void *out, uint32_t log_np, uint32_t log_mout, const void *spow,
+                              cudaStream_t stream, uint64_t *launches);
 // copies salt columns (column-major natural LDE order) into the leaf matrix: leaves[k][col0 + j] = salt[j][bitrev(k)]
 void launch_salt_scatter(int field, const void *salts, uint32_t num_salt, uint32_t log_N, uint64_t row_begin,
                          uint64_t row_count, void *leaves, uint64_t pitch, uint32_t col0, cudaStream_t stream,
