@@ -116,25 +116,45 @@ __device__ __forceinline__ u64 gl_mul_add(u64 a, u64 b, u64 c) {
 
 __device__ __forceinline__ u64 gl_canon(u64 a) { return a >= P2G_GL_P ? a - P2G_GL_P : a; }
 
-// a + b for arbitrary representatives (two possible wrap corrections)
+// a + b for arbitrary representatives: 2^64 = EPS, so a carry folds back in as +EPS; that can carry once more
+// (only when both inputs were >= p), never a third time.
 __device__ __forceinline__ u64 gl_add(u64 a, u64 b) {
-    u64 s = a + b;
-    if (s < a) {
-        u64 t = s + P2G_GL_EPS;
-        if (t < s) t += P2G_GL_EPS;
-        s = t;
-    }
-    return s;
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), s0, s1;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        "add.cc.u32 %0, %2, %4;\n\t"
+        "addc.cc.u32 %1, %3, %5;\n\t"
+        "addc.u32 m, 0, 0;\n\t"           // carry
+        "sub.u32 m, 0, m;\n\t"            // -carry = low word of carry*EPS
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "sub.u32 m, 0, m;\n\t"
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(s0), "=&r"(s1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return gl_pack(s0, s1);
 }
-// a - b for arbitrary representatives
+// a - b for arbitrary representatives: a borrow folds back in as -EPS (= subtracting the mask 0xffffffff from the low
+// word with borrow propagation), at most twice.
 __device__ __forceinline__ u64 gl_sub(u64 a, u64 b) {
-    u64 d = a - b;
-    if (a < b) {
-        u64 t = d - P2G_GL_EPS;
-        if (t > d) t -= P2G_GL_EPS;
-        d = t;
-    }
-    return d;
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), d0, d1;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"          // m = -borrow
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(d0), "=&r"(d1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return gl_pack(d0, d1);
 }
 // a + b where b is canonical (< p): a single correction is exact (a + b < 2^64 + p)
 __device__ __forceinline__ u64 gl_add_c(u64 a, u64 b) {
