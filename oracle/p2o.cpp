@@ -34,24 +34,30 @@ struct GL {
     static constexpr unsigned DIGEST_ELEMS = 4;
     static constexpr unsigned WIDTH = 12;
 
-    static inline E reduce128(u128 x) {
-        // same identity the reference uses (poseidon_goldilocks.rs:254-268): 2^64 = EPS, 2^96 = -1 (mod P)
+    // same identity the reference uses (poseidon_goldilocks.rs:254-268): 2^64 = EPS, 2^96 = -1 (mod P).
+    // Branch-free (the carry of t0 + t1 is a coin flip, a branch there mispredicts half the time); result < 2^64,
+    // not necessarily canonical.
+    static inline uint64_t reduce128_weak(u128 x) {
         uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
         uint64_t hi_hi = hi >> 32, hi_lo = hi & EPS;
         uint64_t t0 = lo - hi_hi;
-        if (lo < hi_hi) t0 -= EPS;
+        t0 -= EPS & (0 - (uint64_t)(lo < hi_hi));
         uint64_t t1 = hi_lo * EPS;
         uint64_t t2 = t0 + t1;
-        if (t2 < t1) t2 += EPS;
-        if (t2 >= P) t2 -= P;
+        t2 += EPS & (0 - (uint64_t)(t2 < t1));
         return t2;
     }
-    static inline E add(E a, E b) {
-        uint64_t s = a + b;
-        if (s < a || s >= P) s -= P;
-        return s;
+    static inline E reduce128(u128 x) {
+        uint64_t t2 = reduce128_weak(x);
+        return t2 - (P & (0 - (uint64_t)(t2 >= P)));
     }
-    static inline E sub(E a, E b) { return a >= b ? a - b : a + (P - b); }
+    // product of arbitrary 64-bit representatives, result an arbitrary representative (used inside the permutation)
+    static inline uint64_t mul_weak(uint64_t a, uint64_t b) { return reduce128_weak((u128)a * b); }
+    static inline E add(E a, E b) {  // canonical in, canonical out, branch-free
+        uint64_t s = a + b;
+        return s - (P & (0 - (uint64_t)((s < a) | (s >= P))));
+    }
+    static inline E sub(E a, E b) { return a - b + (P & (0 - (uint64_t)(a < b))); }
     static inline E mul(E a, E b) { return reduce128((u128)a * b); }
     static inline E from_u64(uint64_t x) { return x >= P ? x - P : x; }
 };
@@ -232,20 +238,33 @@ namespace pgl {
 static const unsigned W = 12, HALF_FULL = 4, N_PARTIAL = 22;
 
 static inline uint64_t sbox(uint64_t x) {  // sbox_monomial :840-846
-    uint64_t x2 = GL::mul(x, x), x4 = GL::mul(x2, x2), x3 = GL::mul(x, x2);
+    uint64_t x2 = GL::mul_weak(x, x), x4 = GL::mul_weak(x2, x2), x3 = GL::mul_weak(x, x2);
     return GL::mul(x3, x4);
 }
 // mds_layer semantics (:497-527 computes the same product through a frequency-domain shortcut;
 // mds_row_shf :547-557 is the definition): out[r] = sum_i circ[i] * s[(i+r)%12] + diag[r]*s[r]
+// Like the reference's mds_layer (:497-527) the product is taken on the 32-bit halves of the state so that every
+// accumulator fits 64 bits; the doubled arrays turn the circulant indexing into plain sliding windows that the
+// compiler vectorises.
 static inline void mds_layer(uint64_t s[W]) {
-    uint64_t out[W];
-    for (unsigned r = 0; r < W; r++) {
-        u128 acc = 0;
-        for (unsigned i = 0; i < W; i++) acc += (u128)s[(i + r) % W] * P2O_GL_MDS_CIRC[i];
-        acc += (u128)s[r] * P2O_GL_MDS_DIAG[r];
-        out[r] = GL::reduce128(acc);
+    alignas(64) uint64_t lo[32], hi[32], acc_lo[16], acc_hi[16];
+    for (unsigned i = 0; i < W; i++) {
+        lo[i] = lo[i + W] = (uint32_t)s[i];
+        hi[i] = hi[i + W] = s[i] >> 32;
     }
-    memcpy(s, out, sizeof(out));
+    for (unsigned i = 2 * W; i < 32; i++) lo[i] = hi[i] = 0;
+    for (unsigned r = 0; r < 16; r++) acc_lo[r] = acc_hi[r] = 0;
+    for (unsigned i = 0; i < W; i++) {
+        const uint64_t c = P2O_GL_MDS_CIRC[i];
+#pragma GCC unroll 16
+        for (unsigned r = 0; r < 16; r++) {  // 16 lanes (12 used): two AVX-512 or four AVX2 vectors per half
+            acc_lo[r] += lo[r + i] * c;
+            acc_hi[r] += hi[r + i] * c;
+        }
+    }
+    acc_lo[0] += lo[0] * P2O_GL_MDS_DIAG[0];
+    acc_hi[0] += hi[0] * P2O_GL_MDS_DIAG[0];
+    for (unsigned r = 0; r < W; r++) s[r] = GL::reduce128((u128)acc_lo[r] + ((u128)acc_hi[r] << 32));
 }
 static inline void constant_layer(uint64_t s[W], unsigned round) {
     for (unsigned i = 0; i < W; i++) s[i] = GL::add(s[i], GL::from_u64(P2O_GL_POSEIDON_RC[i + W * round]));
