@@ -388,6 +388,12 @@ __global__ void leaves_to_columns_kernel(const E *__restrict__ leaves, u64 pitch
 }
 
 // ---- launchers ---------------------------------------------------------------------------------
+// one thread per 16 tile elements (a 4-stage round gives every thread exactly one unit), between 64 and 256 threads
+static unsigned block_threads(u64 tile_elems) {
+    u64 t = tile_elems >> 4;
+    return (unsigned)(t < 64 ? 64 : (t > 256 ? 256 : t));
+}
+
 template <class F>
 static void launch_pass_t(int kind, const NttPass &p, cudaStream_t stream, uint64_t *launches) {
     typedef typename F::E E;
@@ -402,7 +408,7 @@ static void launch_pass_t(int kind, const NttPass &p, cudaStream_t stream, uint6
             cudaFuncSetAttribute(ntt_strided_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr_set = true;
         }
-        ntt_strided_kernel<F><<<(unsigned)(tiles_per_col * p.num_cols), 256, smem, stream>>>(p);
+        ntt_strided_kernel<F><<<(unsigned)(tiles_per_col * p.num_cols), block_threads((u64)np << lw), smem, stream>>>(p);
     } else if (kind == NTT_FINAL_NATURAL) {
         u32 lc = p.log_n - lp;
         u32 lw = lc < (u32)F::W_LOG ? lc : (u32)F::W_LOG;
@@ -413,7 +419,7 @@ static void launch_pass_t(int kind, const NttPass &p, cudaStream_t stream, uint6
             cudaFuncSetAttribute(ntt_final_natural_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr_set = true;
         }
-        ntt_final_natural_kernel<F><<<(unsigned)(groups * p.num_cols), 256, smem, stream>>>(p);
+        ntt_final_natural_kernel<F><<<(unsigned)(groups * p.num_cols), block_threads((u64)np << lw), smem, stream>>>(p);
     } else {
         u32 lc = p.log_n - lp;
         size_t smem = ((size_t)(np + F::PAD) * (1u << F::W_LOG) + (np >> 1)) * sizeof(E);
@@ -423,7 +429,7 @@ static void launch_pass_t(int kind, const NttPass &p, cudaStream_t stream, uint6
             cudaFuncSetAttribute(ntt_final_leaves_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr_set = true;
         }
-        ntt_final_leaves_kernel<F><<<(unsigned)(col_groups << lc), 256, smem, stream>>>(p);
+        ntt_final_leaves_kernel<F><<<(unsigned)(col_groups << lc), block_threads((u64)np << F::W_LOG), smem, stream>>>(p);
     }
     ++*launches;
 }
