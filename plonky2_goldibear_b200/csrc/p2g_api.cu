@@ -72,7 +72,11 @@ struct p2g_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // D2H of finished outputs overlaps the hashing kernels
     cudaEvent_t ev[8];
-    cudaEvent_t ready[64];               // "rows of coset b are final" / "coefficients are final" markers
+    cudaStream_t h2d_stream = nullptr;   // H2D of the next column group overlaps the transforms of the current one
+    cudaEvent_t ready[64];               // "rows are final" markers for the copy stream
+    enum { MAX_GROUPS = 32 };
+    cudaEvent_t gready[MAX_GROUPS + 1], gdone[MAX_GROUPS];  // column group arrived / its coefficients are final
+    cudaEvent_t tev[3 * MAX_GROUPS];     // stage timing per column group
     std::mutex mu;
     std::string error;
     uint64_t launches = 0;
@@ -364,6 +368,10 @@ int32_t p2g_init(const int32_t *device_ids, int32_t n_devices, p2g_ctx **out_ctx
         return P2G_ERR_NO_DEVICE;
     }
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
+    for (auto &ev : ctx->gready) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto &ev : ctx->gdone) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto &ev : ctx->tev) cudaEventCreate(&ev);
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     for (auto &ev : ctx->ready) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     static PoseidonGlTables gl_tables;
@@ -392,6 +400,10 @@ void p2g_destroy(p2g_ctx *ctx) {
     drop_pass_tables(ctx);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->ready) cudaEventDestroy(ev);
+    for (auto &ev : ctx->gready) cudaEventDestroy(ev);
+    for (auto &ev : ctx->gdone) cudaEventDestroy(ev);
+    for (auto &ev : ctx->tev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->h2d_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -504,66 +516,89 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         d_cap = ctx->cap.ptr;
     }
 
-    // ---- H2D
+    // ---- H2D, "IFFT", "FFT + blinding" + "transpose LDEs"
+    // Columns are independent until the leaves are hashed, so with pinned host input they are processed in groups:
+    // group g+1 crosses PCIe (h2d stream) while group g runs its inverse NTT and its 2^rate_bits coset NTTs, and the
+    // coefficients of a finished group start their way home (d2h stream).  Device input / pageable memory = one group.
     CK(cudaEventRecord(ctx->ev[0], st));
-    void *d_input;
-    if (dev_in) {
-        d_input = const_cast<void *>(d->col_ptrs[0]);
-        if (d->input_kind == P2G_INPUT_VALUES) {
-            // the inverse transform runs in place on its input: work on a copy, the caller keeps its buffer
-            CK(cudaMemcpyAsync(ctx->in.ptr, d_input, (size_t)c * col_bytes, cudaMemcpyDeviceToDevice, st));
-            d_input = ctx->in.ptr;
-        }
-    } else {
-        for (unsigned j = 0; j < c; j++) {
-            if (!d->col_ptrs[j]) return ctx->fail(P2G_ERR_INVALID, "col_ptrs[%u] is NULL", j);
-            CK(cudaMemcpyAsync((char *)ctx->in.ptr + (size_t)j * col_bytes, d->col_ptrs[j], col_bytes, cudaMemcpyHostToDevice, st));
-        }
+    cudaStream_t cs = ctx->copy_stream, hs = ctx->h2d_stream;
+    const bool overlap_d2h = !dev_out;
+    const bool values = d->input_kind == P2G_INPUT_VALUES;
+    const unsigned tile_cols = f.id == FIELD_GL ? 8 : 16;
+    bool pipelined = !dev_in && c > 2 * tile_cols && is_pinned(d->col_ptrs[0]) && is_pinned(d->col_ptrs[c - 1]);
+    unsigned group_cols = c;
+    if (pipelined) {
+        group_cols = 2 * tile_cols;
+        while ((c + group_cols - 1) / group_cols > p2g_ctx::MAX_GROUPS) group_cols += 2 * tile_cols;
+    }
+    const unsigned num_groups = (c + group_cols - 1) / group_cols;
+    const bool coeffs_early = overlap_d2h && values && d->coeffs_out && is_pinned(d->coeffs_out[0]) && is_pinned(d->coeffs_out[c - 1]);
+    const bool coeffs_sent = coeffs_early;
+    void *d_input = dev_in ? const_cast<void *>(d->col_ptrs[0]) : ctx->in.ptr;
+    if (dev_in && values) {
+        // the inverse transform runs in place on its input: work on a copy, the caller keeps its buffer
+        CK(cudaMemcpyAsync(ctx->in.ptr, d_input, (size_t)c * col_bytes, cudaMemcpyDeviceToDevice, st));
         d_input = ctx->in.ptr;
     }
+    if (!dev_in)
+        for (unsigned j = 0; j < c; j++)
+            if (!d->col_ptrs[j]) return ctx->fail(P2G_ERR_INVALID, "col_ptrs[%u] is NULL", j);
     if (salt) {
         if ((rc = ensure(ctx, ctx->salts, (size_t)salt * N * f.elem))) return rc;
         for (unsigned j = 0; j < salt; j++)
             CK(cudaMemcpyAsync((char *)ctx->salts.ptr + (size_t)j * N * f.elem, d->salt_ptrs[j], N * f.elem,
                                dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     }
-    CK(cudaEventRecord(ctx->ev[1], st));
-
-    // ---- "IFFT"
     void *d_coeffs = d_input;
-    if (d->input_kind == P2G_INPUT_VALUES) {
-        void *dst = (dev_out && d->coeffs_out && d->coeffs_out[0]) ? d->coeffs_out[0] : ctx->coeffs.ptr;
-        if ((rc = run_transform(ctx, f, repr, true, L, c, d_input, nullptr, dst, n, 0, 0))) return rc;
-        d_coeffs = dst;
-    }
-    CK(cudaEventRecord(ctx->ev[2], st));
-    cudaStream_t cs = ctx->copy_stream;
-    const bool overlap_d2h = !dev_out;
-    bool coeffs_sent = false;
-    if (overlap_d2h && d->input_kind == P2G_INPUT_VALUES && d->coeffs_out && is_pinned(d->coeffs_out[0]) &&
-        is_pinned(d->coeffs_out[c - 1])) {
-        coeffs_sent = true;
-        // `polynomials` are final now: send them home while the LDE and the hashing run
-        CK(cudaEventRecord(ctx->ready[63], st));
-        CK(cudaStreamWaitEvent(cs, ctx->ready[63], 0));
-        for (unsigned j = 0; j < c; j++)
-            if (d->coeffs_out[j])
-                CK(cudaMemcpyAsync(d->coeffs_out[j], (char *)d_coeffs + (size_t)j * col_bytes, col_bytes, cudaMemcpyDeviceToHost, cs));
-    }
-
-    // ---- "FFT + blinding" + "transpose LDEs": one coset of n rows at a time, written straight into leaf order
+    if (values) d_coeffs = (dev_out && d->coeffs_out && d->coeffs_out[0]) ? d->coeffs_out[0] : ctx->coeffs.ptr;
     const uint64_t g = f.generator;
     const uint64_t wN = two_adic_generator(f, LN);
+    if (pipelined) {
+        // the h2d stream must not overwrite the input buffer while earlier work of this context still reads it
+        CK(cudaEventRecord(ctx->gready[p2g_ctx::MAX_GROUPS], st));
+        CK(cudaStreamWaitEvent(hs, ctx->gready[p2g_ctx::MAX_GROUPS], 0));
+    }
+    for (unsigned gi2 = 0; gi2 < num_groups; gi2++) {
+        const unsigned col0 = gi2 * group_cols, ncol = std::min(group_cols, c - col0);
+        char *g_in = (char *)d_input + (size_t)col0 * col_bytes;
+        char *g_co = (char *)d_coeffs + (size_t)col0 * col_bytes;
+        if (!dev_in) {
+            cudaStream_t up = pipelined ? hs : st;
+            for (unsigned j = col0; j < col0 + ncol; j++)
+                CK(cudaMemcpyAsync((char *)ctx->in.ptr + (size_t)j * col_bytes, d->col_ptrs[j], col_bytes, cudaMemcpyHostToDevice, up));
+            if (pipelined) {
+                CK(cudaEventRecord(ctx->gready[gi2], hs));
+                CK(cudaStreamWaitEvent(st, ctx->gready[gi2], 0));
+            }
+        }
+        if (gi2 == 0) CK(cudaEventRecord(ctx->ev[1], st));
+        CK(cudaEventRecord(ctx->tev[3 * gi2], st));
+        if (values)
+            if ((rc = run_transform(ctx, f, repr, true, L, ncol, g_in, nullptr, g_co, n, 0, 0))) return rc;
+        CK(cudaEventRecord(ctx->tev[3 * gi2 + 1], st));
+        if (coeffs_early) {
+            // `polynomials` of this group are final: send them home while the LDE and the hashing run
+            CK(cudaEventRecord(ctx->gdone[gi2], st));
+            CK(cudaStreamWaitEvent(cs, ctx->gdone[gi2], 0));
+            for (unsigned j = col0; j < col0 + ncol; j++)
+                if (d->coeffs_out[j])
+                    CK(cudaMemcpyAsync(d->coeffs_out[j], (char *)d_coeffs + (size_t)j * col_bytes, col_bytes, cudaMemcpyDeviceToHost, cs));
+        }
+        // one coset of n rows at a time, written straight into leaf order
+        for (unsigned b = 0; b < cosets_local; b++) {
+            uint64_t shift = f_mul(f, g, f_pow(f, wN, bitrev(coset0 + b, r)));
+            if ((rc = run_transform(ctx, f, repr, false, L, ncol, g_co, (char *)ctx->tmp.ptr + (size_t)col0 * col_bytes,
+                                    (char *)d_leaves + (size_t)col0 * f.elem, pitch_dev, shift, (uint64_t)b * n)))
+                return rc;
+        }
+        CK(cudaEventRecord(ctx->tev[3 * gi2 + 2], st));
+    }
     const bool leaves_early = overlap_d2h && want_leaves && !salt && cosets_local <= 62 && is_pinned(d->leaves_out);
-    for (unsigned b = 0; b < cosets_local; b++) {
-        unsigned bg = coset0 + b;
-        uint64_t shift = f_mul(f, g, f_pow(f, wN, bitrev(bg, r)));
-        if ((rc = run_transform(ctx, f, repr, false, L, c, d_coeffs, ctx->tmp.ptr, d_leaves, pitch_dev, shift, (uint64_t)b * n)))
-            return rc;
-        if (leaves_early && b < 62) {
-            // rows [b*n, (b+1)*n) are final (no salt columns to add): start their D2H now
-            CK(cudaEventRecord(ctx->ready[b], st));
-            CK(cudaStreamWaitEvent(cs, ctx->ready[b], 0));
+    if (leaves_early) {
+        // every row is final (no salt columns to add): start the D2H of the leaves, one coset per copy
+        CK(cudaEventRecord(ctx->ready[0], st));
+        CK(cudaStreamWaitEvent(cs, ctx->ready[0], 0));
+        for (unsigned b = 0; b < cosets_local; b++) {
             char *src = (char *)d_leaves + (size_t)b * n * pitch_dev * f.elem;
             char *dsth = (char *)d->leaves_out + (size_t)b * n * out_pitch * f.elem;
             if (out_pitch == pitch_dev)
@@ -608,9 +643,14 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     CK(cudaEventRecord(ctx->ev[5], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(cs));
-    d->h2d_seconds = ev_seconds(ctx->ev[0], ctx->ev[1]);
-    d->stage_seconds[0] = ev_seconds(ctx->ev[1], ctx->ev[2]);
-    d->stage_seconds[1] = ev_seconds(ctx->ev[2], ctx->ev[3]);
+    CK(cudaStreamSynchronize(hs));
+    d->h2d_seconds = ev_seconds(ctx->ev[0], ctx->ev[1]);  // exposed part: until the first group is on the device
+    d->stage_seconds[0] = d->stage_seconds[1] = 0.0;
+    for (unsigned gi2 = 0; gi2 < num_groups; gi2++) {
+        d->stage_seconds[0] += ev_seconds(ctx->tev[3 * gi2], ctx->tev[3 * gi2 + 1]);
+        d->stage_seconds[1] += ev_seconds(ctx->tev[3 * gi2 + 1], ctx->tev[3 * gi2 + 2]);
+    }
+    d->stage_seconds[1] += ev_seconds(ctx->tev[3 * (num_groups - 1) + 2], ctx->ev[3]);  // salt scatter
     d->stage_seconds[2] = 0.0;
     d->stage_seconds[3] = ev_seconds(ctx->ev[3], ctx->ev[4]);
     d->d2h_seconds = ev_seconds(ctx->ev[4], ctx->ev[5]);
