@@ -150,7 +150,7 @@ def workload_config(args, field_name):
             "cap_height": args.cap_height, "parallelism": "coset-sharded x%d" % args.gpus if args.gpus > 1 else "single GPU",
             "l2": "inputs (%.2f GB) and leaves (%.2f GB) are larger than the 126 MB L2; no flush needed" % (
                 args.cols * (1 << args.log_n) * (8 if field_name == "gl" else 4) / 1e9,
-                args.cols * (8 << args.log_n) * (8 if field_name == "gl" else 4) / 1e9)}
+                args.cols * ((1 << args.rate_bits) << args.log_n) * (8 if field_name == "gl" else 4) / 1e9)}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -358,12 +358,27 @@ def run_ours(args, field_name):
     roofline_ntt = {"kernels": "ntt_strided_kernel + ntt_final_natural_kernel + ntt_final_leaves_kernel", "bound": "hbm",
                     "achieved": ntt_bytes / t_ntt / 1e9, "peak": peak, "unit": "GB/s", "frac": ntt_bytes / t_ntt / 1e9 / peak,
                     "ms": t_ntt * 1e3, "algorithmic_gb": ntt_bytes / 1e9}
+    # integer-pipe view of the dominant kernel: issue cycles spent per warp-permutation against the SASS cost model
+    int_pipe = None
+    try:
+        model = json.load(open(os.path.join(ROOT, "profiles", "r1_leaf_sponge_cost_model.json")))
+        key = "goldilocks_poseidon" if field_name == "gl" else "babybear_poseidon2"
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        clk = (clocks or {}).get("sm_mhz") or 1965.0
+        leaf_perms = rows_local * ((c + 7) // 8)
+        measured = t_leaf * sms * 4 * clk * 1e6 / (leaf_perms / 32.0)
+        int_pipe = {"kernel": "leaf_hash_kernel", "issue_cycles_per_warp_permutation": measured,
+                    "model_cycles_per_warp_permutation": model[key]["cycles_per_warp_permutation"],
+                    "issue_slot_utilisation_vs_model": model[key]["cycles_per_warp_permutation"] / measured,
+                    "model": "profiles/r1_leaf_sponge_cost_model.json (IMAD.WIDE/HI 3.6, IMAD 2, other 1 issue cycles; tools/microbench/imad_probe.cu)"}
+    except Exception as e:  # the model file is evidence, not a dependency
+        int_pipe = {"unavailable": str(e)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64" if field_name == "gl" else "u32", "data": "synthetic",
         "config": workload_config(args, field_name), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_ntt": roofline_ntt,
+        "roofline": roofline, "roofline_ntt": roofline_ntt, "int_pipe": int_pipe,
         "stage_ms": {"inverse_ntt": ksec[0] * 1e3, "lde_ntt": ksec[1] * 1e3, "leaf_sponge": ksec[2] * 1e3, "tree_levels": ksec[3] * 1e3},
         "hash": {"permutations_per_step": int(perms), "permutations_per_s": perms / G / (ksec[2] + ksec[3])},
     }
