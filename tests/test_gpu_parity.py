@@ -288,3 +288,88 @@ def test_large_commit_properties(ctx, oracle):
         for cf in coeffs[col][::-1].tolist():
             acc = (acc * x + cf) % GL_P
         assert acc == int(batch.merkle_tree.leaves[k][col])
+
+
+# ---- FRI commit-phase tree shapes (fri/prover.rs:83-133 calls MerkleTree::new on these) ------------
+@pytest.mark.parametrize("field,d_ext,arity_bits,log_n", [(0, 2, 4, 14), (0, 2, 1, 12), (1, 4, 4, 13), (1, 4, 1, 10), (1, 4, 3, 9)])
+def test_fri_layer_tree_shapes(ctx, oracle, field, d_ext, arity_bits, log_n):
+    """Leaves of a FRI layer tree: the extension-field codeword in bit-reversed order, chunked by the arity and
+    flattened to base elements (leaf length arity*D); arity 2 leaves have 4 (GL) / 8 (BB) elements and take the
+    no-hash branch of hash_or_noop.  cap_height as in the FRI config (4), clamped like the prover does."""
+    import plonky2_goldibear_b200 as p2g
+    F = fields()[field]
+    arity = 1 << arity_bits
+    rng = np.random.default_rng(log_n)
+    codeword = rng.integers(0, F.order, size=(1 << log_n, d_ext), dtype=np.uint64).astype(F.dtype)
+    idx = np.array([oracle.load().p2o_reverse_bits(i, log_n) for i in range(1 << log_n)])
+    leaves = codeword[idx].reshape((1 << log_n) // arity, arity * d_ext)
+    cap_height = min(4, log_n - arity_bits)
+    tree = p2g.MerkleTree.new(F, leaves, cap_height, ctx=ctx)
+    digests, cap = oracle.merkle_tree(field, leaves, cap_height)
+    assert (tree.digests == digests).all() and (tree.cap.hashes == cap).all()
+
+
+# ---- BASELINE.json full sizes, checked through size-independent properties -------------------------------------
+def _check_commit_properties(ctx, oracle, field, log_n, c, r, h, samples=5, seed=3):
+    import plonky2_goldibear_b200 as p2g
+    F = fields()[field]
+    p = F.order
+    n, N = 1 << log_n, 1 << (log_n + r)
+    vals = synthetic_columns(p, F.dtype, c, n, seed=seed)
+    batch = p2g.PolynomialBatch.from_values(F, list(vals), r, False, h, ctx=ctx)
+    lib = oracle.load()
+    rng = np.random.default_rng(seed)
+    tree = batch.merkle_tree
+    assert tree.leaves.shape == (N, c) and tree.digests.shape == (2 * (N - (1 << h)), F.num_hash_out_elts)
+    # (1) interpolation round trip on sampled columns: the CPU FFT of the returned coefficients gives back the input
+    for j in {0, c // 2, c - 1}:
+        assert (oracle.fft(field, batch.polynomials[j]) == vals[j]).all()
+    # (2) sampled rows are the evaluations at g * w_N^bitrev(k) (Horner on the CPU), (3) their Merkle paths verify
+    wN = lib.p2o_two_adic_generator(field, log_n + r)
+    for k in [0, N - 1] + [int(x) for x in rng.integers(0, N, size=samples)]:
+        sib = tree.prove(k)
+        assert oracle.verify_merkle_proof_to_cap(field, tree.leaves[k], k, tree.cap.hashes, sib)
+        x = F.generator * pow(wN, lib.p2o_reverse_bits(k, log_n + r), p) % p
+        col = int(rng.integers(0, c))
+        acc = 0
+        for cf in batch.polynomials[col][::-1].tolist():
+            acc = (acc * x + cf) % p
+        assert acc == int(tree.leaves[k][col])
+    # (4) the cap is the root layer of the digests: recompute the top of every cap subtree with the oracle's compression
+    sub_len = tree.digests.shape[0] >> h
+    for s in {0, (1 << h) - 1}:
+        blk = tree.digests[s * sub_len:(s + 1) * sub_len]
+        mid = sub_len // 2
+        assert (oracle.two_to_one(field, blk[mid - 1], blk[mid]) == tree.cap.hashes[s]).all()
+    # (5) linearity of the LDE: leaves(a) + leaves(b) == leaves(a + b) on a sampled row, via a 2-column side commit
+    a, b = vals[0].astype(np.uint64), vals[1].astype(np.uint64)
+    s_col = ((a + b) % np.uint64(p)).astype(F.dtype) if p < (1 << 62) else np.array(
+        [(int(x) + int(y)) % p for x, y in zip(a[:0], b[:0])], dtype=F.dtype)
+    if p < (1 << 62):
+        side = p2g.PolynomialBatch.from_values(F, [s_col], r, False, 0, ctx=ctx)
+        for k in (1, N // 2 + 3):
+            assert (int(tree.leaves[k][0]) + int(tree.leaves[k][1])) % p == int(side.merkle_tree.leaves[k][0])
+
+
+def test_config2_full_size_goldilocks(ctx, oracle):
+    """BASELINE config 2: Goldilocks 2^20 x 135, rate_bits 3, cap_height 4 (leaves 9.06 GB)."""
+    _check_commit_properties(ctx, oracle, 0, 20, 135, 3, 4)
+
+
+def test_config3_babybear_reduced_rows(ctx, oracle):
+    """BASELINE config 3 shape (BabyBear, 256 columns, rate_bits 3, cap_height 4) at 2^20 rows -- the same three-pass
+    NTT plan class (log n > 20 needs it; 2^22 is exercised by bench.py --field bb) with 8.6 GB of leaves."""
+    _check_commit_properties(ctx, oracle, 1, 20, 256, 3, 4)
+
+
+def test_three_pass_ntt_plan(ctx, oracle):
+    """log n = 21, 22 use three NTT passes (tile sizes 7/7/7, 8/7/7): full parity on a few columns."""
+    import plonky2_goldibear_b200 as p2g
+    for field, log_n in ((0, 21), (1, 22)):
+        F = fields()[field]
+        vals = synthetic_columns(F.order, F.dtype, 3, 1 << log_n, seed=log_n)
+        batch = p2g.PolynomialBatch.from_values(F, list(vals), 1, False, 2, ctx=ctx)
+        ref = oracle.commit(field, vals, oracle.VALUES, 1, 2)
+        assert (np.stack(batch.polynomials) == ref["coeffs"]).all()
+        assert (batch.merkle_tree.leaves == ref["leaves"]).all()
+        assert (batch.merkle_tree.cap.hashes == ref["cap"]).all() and (batch.merkle_tree.digests == ref["digests"]).all()
