@@ -73,6 +73,12 @@ void p2g_host_free(p2g_ctx *ctx, void *ptr);
 #define P2G_FLAG_DEVICE_INPUT 1u   /* col_ptrs[0] is a DEVICE pointer to the whole column-major [num_cols][n] block */
 #define P2G_FLAG_DEVICE_OUTPUT 2u  /* *_out pointers are DEVICE pointers (coeffs_out[0] = whole block) */
 #define P2G_FLAG_NO_LEAVES_OUT 4u  /* do not return leaves (benchmarks / callers that only need the cap) */
+#define P2G_FLAG_KEEP_ON_DEVICE 8u /* leaves, digests and coefficients stay in device memory owned by a batch handle
+                                      (desc->batch_out); only the cap comes back.  Rows, Merkle paths and whole arrays
+                                      are then fetched on demand (p2g_batch_*): the device-resident form of
+                                      get_lde_values / MerkleTree::get / MerkleTree::prove */
+
+typedef struct p2g_batch p2g_batch;
 
 /* One call = one PolynomialBatch::from_values (input_kind VALUES) or from_coeffs (COEFFS). */
 typedef struct {
@@ -109,9 +115,22 @@ typedef struct {
     /* finer split of the same device time: [0] inverse-NTT passes, [1] LDE NTT passes (+ salt scatter),
      * [2] leaf sponge kernel, [3] tree-level kernels */
     double kernel_seconds[4];
+    p2g_batch **batch_out;   /* with P2G_FLAG_KEEP_ON_DEVICE: receives the handle (free with p2g_batch_free) */
 } p2g_commit_desc;
 
 int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *desc);
+
+/* Device-resident batch accessors.  Indices are leaf indices of the (shard-local) tree, i.e. already bit-reversed
+ * like MerkleTree::get / prove expect (oracle.rs:153-158 does the reverse_bits before indexing).
+ *   get_rows : rows_out[i][0..width) = leaves[row_indices[i]]                    (MerkleTree::get, merkle_tree.rs:183-185)
+ *   prove    : siblings_out[i][layer] = sibling digest of leaf_indices[i]        (MerkleTree::prove, merkle_tree.rs:188-222)
+ *   download : the whole array: what = 0 leaves [rows][width], 1 digests, 2 cap, 3 coefficients [num_cols][n] */
+int32_t p2g_batch_get_rows(p2g_ctx *ctx, p2g_batch *batch, const uint64_t *row_indices, uint64_t count, void *rows_out);
+int32_t p2g_batch_prove(p2g_ctx *ctx, p2g_batch *batch, const uint64_t *leaf_indices, uint64_t count, void *siblings_out);
+int32_t p2g_batch_download(p2g_ctx *ctx, p2g_batch *batch, int32_t what, void *out);
+/* shape of the batch: rows, width (elements per leaf), num_layers (siblings per proof), cap entries */
+int32_t p2g_batch_shape(p2g_batch *batch, uint64_t *rows, uint64_t *width, uint32_t *num_layers, uint64_t *num_cap);
+void p2g_batch_free(p2g_ctx *ctx, p2g_batch *batch);
 
 /* MerkleTree::new alone (merkle_tree.rs:152-181), e.g. for the FRI commit-phase trees (fri/prover.rs:108). */
 typedef struct {

@@ -11,6 +11,7 @@ _LOCK = threading.Lock()
 FLAG_DEVICE_INPUT = 1
 FLAG_DEVICE_OUTPUT = 2
 FLAG_NO_LEAVES_OUT = 4
+FLAG_KEEP_ON_DEVICE = 8
 
 ERR_NAMES = {0: "OK", -1: "INVALID", -2: "NO_DEVICE", -3: "CUDA", -4: "OOM", -5: "UNSUPPORTED"}
 
@@ -31,7 +32,7 @@ class CommitDesc(ctypes.Structure):
         ("leaf_pitch", ctypes.c_uint64), ("digests_out", ctypes.c_void_p), ("cap_out", ctypes.c_void_p),
         ("shard_index", ctypes.c_uint32), ("shard_count", ctypes.c_uint32),
         ("stage_seconds", ctypes.c_double * 4), ("h2d_seconds", ctypes.c_double), ("d2h_seconds", ctypes.c_double),
-        ("kernel_seconds", ctypes.c_double * 4),
+        ("kernel_seconds", ctypes.c_double * 4), ("batch_out", ctypes.POINTER(ctypes.c_void_p)),
     ]
 
 
@@ -47,7 +48,8 @@ class MerkleDesc(ctypes.Structure):
 EXPORTS = [
     "p2g_abi_version", "p2g_init", "p2g_destroy", "p2g_last_error", "p2g_host_alloc", "p2g_host_free", "p2g_commit",
     "p2g_merkle", "p2g_merkle_finish_cap", "p2g_permute", "p2g_transform", "p2g_workspace_bytes",
-    "p2g_release_workspace", "p2g_stream", "p2g_kernel_launches",
+    "p2g_release_workspace", "p2g_stream", "p2g_kernel_launches", "p2g_batch_get_rows", "p2g_batch_prove",
+    "p2g_batch_download", "p2g_batch_shape", "p2g_batch_free",
 ]
 
 
@@ -97,6 +99,16 @@ def load_library() -> ctypes.CDLL:
         lib.p2g_stream.restype = vp
         lib.p2g_kernel_launches.argtypes = [vp]
         lib.p2g_kernel_launches.restype = u64
+        lib.p2g_batch_get_rows.argtypes = [vp, vp, vp, u64, vp]
+        lib.p2g_batch_get_rows.restype = i32
+        lib.p2g_batch_prove.argtypes = [vp, vp, vp, u64, vp]
+        lib.p2g_batch_prove.restype = i32
+        lib.p2g_batch_download.argtypes = [vp, vp, i32, vp]
+        lib.p2g_batch_download.restype = i32
+        lib.p2g_batch_shape.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(u32), ctypes.POINTER(u64)]
+        lib.p2g_batch_shape.restype = i32
+        lib.p2g_batch_free.argtypes = [vp, vp]
+        lib.p2g_batch_free.restype = None
         _LIB = lib
         return lib
 

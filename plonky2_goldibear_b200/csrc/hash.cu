@@ -148,6 +148,56 @@ __global__ void __launch_bounds__(128) permute_kernel(typename H::W *states, u64
     for (int i = 0; i < H::WIDTH; i++) states[t * H::WIDTH + i] = H::store(s[i]);
 }
 
+// ---- device-resident accessors (MerkleTree::get / MerkleTree::prove on the GPU copy) -----------------------------
+template <class E>
+__global__ void gather_rows_kernel(const E *__restrict__ leaves, u64 pitch, u32 width, const u64 *__restrict__ idx,
+                                   u64 count, E *__restrict__ out) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count * width) return;
+    u64 i = t / width;
+    u32 j = (u32)(t - i * width);
+    out[t] = leaves[idx[i] * pitch + j];
+}
+// one thread per (proof, layer); 32-byte digests moved as two 16-byte words.  Index arithmetic of merkle_tree.rs:200-217.
+__global__ void gather_proofs_kernel(const uint4 *__restrict__ digests, u32 log_leaves, u32 cap_height,
+                                     const u64 *__restrict__ idx, u64 count, uint4 *__restrict__ out) {
+    u32 num_layers = log_leaves - cap_height;
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count * num_layers) return;
+    u64 i = t / num_layers;
+    u32 layer = (u32)(t - i * num_layers);
+    u64 leaf = idx[i];
+    u64 tree_index = leaf >> num_layers;
+    u64 tree_len = 2 * (((u64)1 << num_layers) - 1);
+    u64 pair_index = (leaf & (((u64)1 << num_layers) - 1)) >> layer;
+    u64 parity = pair_index & 1;
+    pair_index >>= 1;
+    u64 siblings_index = (pair_index << (layer + 1)) + ((u64)1 << layer) - 1;
+    u64 slot = tree_len * tree_index + 2 * siblings_index + (1 - parity);
+    out[2 * t] = digests[2 * slot];
+    out[2 * t + 1] = digests[2 * slot + 1];
+}
+
+void launch_gather_rows(int field, const void *leaves, uint64_t pitch, uint32_t width, const uint64_t *idx, uint64_t count,
+                        void *rows_out, cudaStream_t stream, uint64_t *launches) {
+    u64 total = count * width;
+    if (!total) return;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    if (field == FIELD_GL)
+        gather_rows_kernel<u64><<<blocks, 256, 0, stream>>>((const u64 *)leaves, pitch, width, (const u64 *)idx, count, (u64 *)rows_out);
+    else
+        gather_rows_kernel<u32><<<blocks, 256, 0, stream>>>((const u32 *)leaves, pitch, width, (const u64 *)idx, count, (u32 *)rows_out);
+    ++*launches;
+}
+void launch_gather_proofs(const void *digests, uint32_t log_leaves, uint32_t cap_height, const uint64_t *idx,
+                          uint64_t count, void *siblings_out, cudaStream_t stream, uint64_t *launches) {
+    u64 total = count * (log_leaves - cap_height);
+    if (!total) return;
+    gather_proofs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const uint4 *)digests, log_leaves, cap_height,
+                                                                            (const u64 *)idx, count, (uint4 *)siblings_out);
+    ++*launches;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------
 template <class H>
 static void leaf_hash_t(const void *leaves, u64 pitch, u32 len, u64 row_begin, u64 row_count, const TreeShape &tree,

@@ -67,6 +67,17 @@ unsigned bitrev(unsigned x, unsigned bits) {
 
 }  // namespace
 
+// Device-resident result of one commit (P2G_FLAG_KEEP_ON_DEVICE): owns its buffers.
+struct p2g_batch {
+    size_t leaves_bytes = 0, digests_bytes = 0, cap_bytes = 0, coeffs_bytes = 0;
+    int field = 0;
+    size_t elem = 0;
+    uint64_t rows = 0, width = 0, num_cols = 0, n = 0;
+    uint32_t log_leaves = 0, cap_height = 0;
+    uint64_t num_digests = 0, num_cap = 0;
+    void *leaves = nullptr, *digests = nullptr, *cap = nullptr, *coeffs = nullptr;
+};
+
 struct p2g_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -88,6 +99,10 @@ struct p2g_ctx {
     // per-pass factor tables built on the device: (field, kind, log_min, log_np, w base, s base) -> table
     std::map<std::tuple<int, int, unsigned, unsigned, uint64_t, uint64_t>, void *> pass_tables;
     size_t pass_table_bytes = 0;
+    // buffers of freed device-resident batches, reused by the next kept commit (cudaMalloc / cudaFree of multi-GB
+    // blocks costs ~100 ms and synchronises the device)
+    std::vector<Buffer> pool;
+    size_t pool_bytes = 0;
 
     int fail(int code, const char *fmt, ...) {
         char buf[512];
@@ -186,6 +201,44 @@ int get_root_table(p2g_ctx *ctx, const FieldInfo &f, unsigned lp, bool inverse, 
     ctx->root_tables[key] = d;
     *out = d;
     return 0;
+}
+
+void *pool_alloc(p2g_ctx *ctx, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 32);
+    int best = -1;
+    for (size_t i = 0; i < ctx->pool.size(); i++)
+        if (ctx->pool[i].bytes >= bytes && ctx->pool[i].bytes <= bytes + bytes / 2 + 4096 &&
+            (best < 0 || ctx->pool[i].bytes < ctx->pool[best].bytes))
+            best = (int)i;
+    if (best >= 0) {
+        void *p = ctx->pool[best].ptr;
+        ctx->pool_bytes -= ctx->pool[best].bytes;
+        ctx->pool.erase(ctx->pool.begin() + best);
+        return p;
+    }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        // make room and retry once
+        for (auto &b : ctx->pool) cudaFree(b.ptr);
+        ctx->pool.clear();
+        ctx->pool_bytes = 0;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+    }
+    return p;
+}
+void pool_free(p2g_ctx *ctx, void *p, size_t bytes) {
+    if (!p) return;
+    bytes = std::max<size_t>(bytes, 32);
+    if (!ctx || ctx->pool_bytes + bytes > ((size_t)48 << 30) || ctx->pool.size() >= 16) {
+        cudaFree(p);
+        return;
+    }
+    ctx->pool.push_back(Buffer{p, bytes});
+    ctx->pool_bytes += bytes;
 }
 
 void drop_pass_tables(p2g_ctx *ctx) {
@@ -430,13 +483,16 @@ void p2g_host_free(p2g_ctx *ctx, void *ptr) {
 uint64_t p2g_workspace_bytes(p2g_ctx *ctx) {
     if (!ctx) return 0;
     return ctx->in.bytes + ctx->coeffs.bytes + ctx->tmp.bytes + ctx->leaves.bytes + ctx->digests.bytes + ctx->cap.bytes +
-           ctx->salts.bytes + ctx->misc.bytes + ctx->pass_table_bytes;
+           ctx->salts.bytes + ctx->misc.bytes + ctx->pass_table_bytes + ctx->pool_bytes;
 }
 void p2g_release_workspace(p2g_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     drop_pass_tables(ctx);
+    for (auto &pb : ctx->pool) cudaFree(pb.ptr);
+    ctx->pool.clear();
+    ctx->pool_bytes = 0;
     for (Buffer *b : {&ctx->in, &ctx->coeffs, &ctx->tmp, &ctx->leaves, &ctx->digests, &ctx->cap, &ctx->salts, &ctx->misc}) {
         if (b->ptr) cudaFree(b->ptr);
         b->ptr = nullptr;
@@ -480,8 +536,11 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     const uint64_t num_cap_local = (uint64_t)1 << cap_local;
     const uint64_t num_digests_local = 2 * (rows_local - num_cap_local);
     const uint64_t pitch_dev = width;
-    const bool dev_in = d->flags & P2G_FLAG_DEVICE_INPUT, dev_out = d->flags & P2G_FLAG_DEVICE_OUTPUT;
-    const bool want_leaves = !(d->flags & P2G_FLAG_NO_LEAVES_OUT) && d->leaves_out;
+    const bool keep = d->flags & P2G_FLAG_KEEP_ON_DEVICE;
+    if (keep && !d->batch_out) return ctx->fail(P2G_ERR_INVALID, "P2G_FLAG_KEEP_ON_DEVICE needs batch_out");
+    if (keep && (d->flags & P2G_FLAG_DEVICE_OUTPUT)) return ctx->fail(P2G_ERR_INVALID, "KEEP_ON_DEVICE and DEVICE_OUTPUT are exclusive");
+    const bool dev_in = d->flags & P2G_FLAG_DEVICE_INPUT, dev_out = (d->flags & P2G_FLAG_DEVICE_OUTPUT) || keep;
+    const bool want_leaves = keep || (!(d->flags & P2G_FLAG_NO_LEAVES_OUT) && d->leaves_out);
     const uint64_t out_pitch = d->leaf_pitch ? d->leaf_pitch : width;
     if (out_pitch < width) return ctx->fail(P2G_ERR_INVALID, "leaf_pitch smaller than the leaf length");
 
@@ -495,21 +554,65 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         if ((rc = ensure(ctx, ctx->coeffs, (size_t)c * col_bytes))) return rc;
     if (L > MAX_TILE_LOG)
         if ((rc = ensure(ctx, ctx->tmp, (size_t)c * col_bytes))) return rc;
+    // a kept batch owns fresh device buffers instead of borrowing the context's workspace
+    p2g_batch *batch = nullptr;
+    struct BatchGuard {
+        p2g_ctx *ctx;
+        p2g_batch *&b;
+        ~BatchGuard() {
+            if (!b) return;
+            cudaStreamSynchronize(ctx->stream);
+            pool_free(ctx, b->leaves, b->leaves_bytes);
+            pool_free(ctx, b->digests, b->digests_bytes);
+            pool_free(ctx, b->cap, b->cap_bytes);
+            pool_free(ctx, b->coeffs, b->coeffs_bytes);
+            delete b;
+        }
+    } batch_guard{ctx, batch};
+    if (keep) {
+        batch = new p2g_batch();
+        batch->field = f.id;
+        batch->elem = f.elem;
+        batch->rows = rows_local;
+        batch->width = width;
+        batch->num_cols = c;
+        batch->n = n;
+        batch->log_leaves = tree_log;
+        batch->cap_height = cap_local;
+        batch->num_digests = num_digests_local;
+        batch->num_cap = num_cap_local;
+        batch->leaves_bytes = (size_t)rows_local * pitch_dev * f.elem;
+        batch->digests_bytes = num_digests_local * 32;
+        batch->cap_bytes = num_cap_local * 32;
+        batch->coeffs_bytes = (size_t)c * col_bytes;
+        batch->leaves = pool_alloc(ctx, batch->leaves_bytes);
+        batch->digests = pool_alloc(ctx, batch->digests_bytes);
+        batch->cap = pool_alloc(ctx, batch->cap_bytes);
+        batch->coeffs = pool_alloc(ctx, batch->coeffs_bytes);
+        if (!batch->leaves || !batch->digests || !batch->cap || !batch->coeffs)
+            return ctx->fail(P2G_ERR_OOM, "device allocation for the kept batch failed");
+    }
     void *d_leaves = nullptr;
-    if (dev_out && want_leaves && out_pitch == pitch_dev) {
+    if (keep) {
+        d_leaves = batch->leaves;
+    } else if (dev_out && want_leaves && out_pitch == pitch_dev) {
         d_leaves = d->leaves_out;
     } else {
         if ((rc = ensure(ctx, ctx->leaves, (size_t)rows_local * pitch_dev * f.elem))) return rc;
         d_leaves = ctx->leaves.ptr;
     }
     void *d_digests = nullptr, *d_cap = nullptr;
-    if (dev_out && d->digests_out) {
+    if (keep) {
+        d_digests = batch->digests;
+    } else if (dev_out && d->digests_out) {
         d_digests = d->digests_out;
     } else {
         if ((rc = ensure(ctx, ctx->digests, std::max<size_t>(32, num_digests_local * 32)))) return rc;
         d_digests = ctx->digests.ptr;
     }
-    if (dev_out && d->cap_out) {
+    if (keep) {
+        d_cap = batch->cap;
+    } else if (dev_out && d->cap_out) {
         d_cap = d->cap_out;
     } else {
         if ((rc = ensure(ctx, ctx->cap, num_cap_local * 32))) return rc;
@@ -534,7 +637,13 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     const unsigned num_groups = (c + group_cols - 1) / group_cols;
     const bool coeffs_early = overlap_d2h && values && d->coeffs_out && is_pinned(d->coeffs_out[0]) && is_pinned(d->coeffs_out[c - 1]);
     const bool coeffs_sent = coeffs_early;
-    void *d_input = dev_in ? const_cast<void *>(d->col_ptrs[0]) : ctx->in.ptr;
+    // from_coeffs into a kept batch: the coefficients land directly in the batch's own buffer
+    void *h2d_base = (keep && !values) ? batch->coeffs : ctx->in.ptr;
+    void *d_input = dev_in ? const_cast<void *>(d->col_ptrs[0]) : h2d_base;
+    if (dev_in && !values && keep) {
+        CK(cudaMemcpyAsync(batch->coeffs, d_input, (size_t)c * col_bytes, cudaMemcpyDeviceToDevice, st));
+        d_input = batch->coeffs;
+    }
     if (dev_in && values) {
         // the inverse transform runs in place on its input: work on a copy, the caller keeps its buffer
         CK(cudaMemcpyAsync(ctx->in.ptr, d_input, (size_t)c * col_bytes, cudaMemcpyDeviceToDevice, st));
@@ -550,7 +659,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
                                dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     }
     void *d_coeffs = d_input;
-    if (values) d_coeffs = (dev_out && d->coeffs_out && d->coeffs_out[0]) ? d->coeffs_out[0] : ctx->coeffs.ptr;
+    if (values) d_coeffs = keep ? batch->coeffs : ((dev_out && d->coeffs_out && d->coeffs_out[0]) ? d->coeffs_out[0] : ctx->coeffs.ptr);
     const uint64_t g = f.generator;
     const uint64_t wN = two_adic_generator(f, LN);
     if (pipelined) {
@@ -565,7 +674,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         if (!dev_in) {
             cudaStream_t up = pipelined ? hs : st;
             for (unsigned j = col0; j < col0 + ncol; j++)
-                CK(cudaMemcpyAsync((char *)ctx->in.ptr + (size_t)j * col_bytes, d->col_ptrs[j], col_bytes, cudaMemcpyHostToDevice, up));
+                CK(cudaMemcpyAsync((char *)h2d_base + (size_t)j * col_bytes, d->col_ptrs[j], col_bytes, cudaMemcpyHostToDevice, up));
             if (pipelined) {
                 CK(cudaEventRecord(ctx->gready[gi2], hs));
                 CK(cudaStreamWaitEvent(st, ctx->gready[gi2], 0));
@@ -636,6 +745,8 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         if (d->digests_out && num_digests_local)
             CK(cudaMemcpyAsync(d->digests_out, d_digests, num_digests_local * 32, cudaMemcpyDeviceToHost, st));
         if (d->cap_out) CK(cudaMemcpyAsync(d->cap_out, d_cap, num_cap_local * 32, cudaMemcpyDeviceToHost, st));
+    } else if (keep) {
+        if (d->cap_out) CK(cudaMemcpyAsync(d->cap_out, d_cap, num_cap_local * 32, cudaMemcpyDeviceToHost, st));
     } else if (want_leaves && d_leaves != d->leaves_out) {
         CK(cudaMemcpy2DAsync(d->leaves_out, out_pitch * f.elem, d_leaves, pitch_dev * f.elem, width * f.elem, rows_local,
                              cudaMemcpyDeviceToDevice, st));
@@ -658,6 +769,101 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     d->kernel_seconds[1] = d->stage_seconds[1];
     d->kernel_seconds[2] = ev_seconds(ctx->ev[3], ctx->ev[6]);
     d->kernel_seconds[3] = ev_seconds(ctx->ev[6], ctx->ev[4]);
+    if (keep) {
+        *d->batch_out = batch;
+        batch = nullptr;  // ownership passes to the caller
+    }
+    return P2G_OK;
+}
+
+int32_t p2g_batch_shape(p2g_batch *b, uint64_t *rows, uint64_t *width, uint32_t *num_layers, uint64_t *num_cap) {
+    if (!b) return P2G_ERR_INVALID;
+    if (rows) *rows = b->rows;
+    if (width) *width = b->width;
+    if (num_layers) *num_layers = b->log_leaves - b->cap_height;
+    if (num_cap) *num_cap = b->num_cap;
+    return P2G_OK;
+}
+
+void p2g_batch_free(p2g_ctx *ctx, p2g_batch *b) {
+    if (!b) return;
+    if (ctx) {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        pool_free(ctx, b->leaves, b->leaves_bytes);
+        pool_free(ctx, b->digests, b->digests_bytes);
+        pool_free(ctx, b->cap, b->cap_bytes);
+        pool_free(ctx, b->coeffs, b->coeffs_bytes);
+    } else {
+        for (void *q : {b->leaves, b->digests, b->cap, b->coeffs})
+            if (q) cudaFree(q);
+    }
+    delete b;
+}
+
+int32_t p2g_batch_get_rows(p2g_ctx *ctx, p2g_batch *b, const uint64_t *row_indices, uint64_t count, void *rows_out) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!b || (count && (!row_indices || !rows_out))) return P2G_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!count) return P2G_OK;
+    for (uint64_t i = 0; i < count; i++)
+        if (row_indices[i] >= b->rows) return ctx->fail(P2G_ERR_INVALID, "row index %llu out of range", (unsigned long long)row_indices[i]);
+    size_t idx_bytes = count * 8, out_bytes = count * b->width * b->elem;
+    size_t off = (idx_bytes + 255) & ~(size_t)255;
+    int rc = ensure(ctx, ctx->misc, off + std::max<size_t>(out_bytes, 16));
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->misc.ptr, row_indices, idx_bytes, cudaMemcpyHostToDevice, st));
+    launch_gather_rows(b->field, b->leaves, b->width, (uint32_t)b->width, (const uint64_t *)ctx->misc.ptr, count,
+                       (char *)ctx->misc.ptr + off, st, &ctx->launches);
+    CK(cudaGetLastError());
+    if (out_bytes) CK(cudaMemcpyAsync(rows_out, (char *)ctx->misc.ptr + off, out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return P2G_OK;
+}
+
+int32_t p2g_batch_prove(p2g_ctx *ctx, p2g_batch *b, const uint64_t *leaf_indices, uint64_t count, void *siblings_out) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!b || (count && !leaf_indices)) return P2G_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t layers = b->log_leaves - b->cap_height;
+    if (!count || !layers) return P2G_OK;
+    if (!siblings_out) return P2G_ERR_INVALID;
+    for (uint64_t i = 0; i < count; i++)
+        if (leaf_indices[i] >= b->rows) return ctx->fail(P2G_ERR_INVALID, "leaf index %llu out of range", (unsigned long long)leaf_indices[i]);
+    size_t idx_bytes = count * 8, out_bytes = count * layers * 32;
+    size_t off = (idx_bytes + 255) & ~(size_t)255;
+    int rc = ensure(ctx, ctx->misc, off + out_bytes);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->misc.ptr, leaf_indices, idx_bytes, cudaMemcpyHostToDevice, st));
+    launch_gather_proofs(b->digests, b->log_leaves, b->cap_height, (const uint64_t *)ctx->misc.ptr, count,
+                         (char *)ctx->misc.ptr + off, st, &ctx->launches);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(siblings_out, (char *)ctx->misc.ptr + off, out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return P2G_OK;
+}
+
+int32_t p2g_batch_download(p2g_ctx *ctx, p2g_batch *b, int32_t what, void *out) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!b || !out) return P2G_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const void *src;
+    size_t bytes;
+    switch (what) {
+        case 0: src = b->leaves; bytes = (size_t)b->rows * b->width * b->elem; break;
+        case 1: src = b->digests; bytes = (size_t)b->num_digests * 32; break;
+        case 2: src = b->cap; bytes = (size_t)b->num_cap * 32; break;
+        case 3: src = b->coeffs; bytes = (size_t)b->num_cols * b->n * b->elem; break;
+        default: return ctx->fail(P2G_ERR_INVALID, "unknown array %d", what);
+    }
+    if (bytes) CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return P2G_OK;
 }
 

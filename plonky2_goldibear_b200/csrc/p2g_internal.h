@@ -33,6 +33,11 @@ void launch_leaf_hash(int field, int repr, const void *leaves, uint64_t pitch_el
                       uint64_t *launches);
 // all inner levels (two_to_one) up to the cap
 void launch_tree_levels(int field, int repr, const TreeShape &tree, cudaStream_t stream, uint64_t *launches);
+// device-resident accessors: rows_out[i][:] = leaves[idx[i]][:width];  siblings_out[i][layer] = sibling digest
+void launch_gather_rows(int field, const void *leaves, uint64_t pitch, uint32_t width, const uint64_t *idx, uint64_t count,
+                        void *rows_out, cudaStream_t stream, uint64_t *launches);
+void launch_gather_proofs(const void *digests, uint32_t log_leaves, uint32_t cap_height, const uint64_t *idx,
+                          uint64_t count, void *siblings_out, cudaStream_t stream, uint64_t *launches);
 // permutation of `count` states in place (device pointer)
 void launch_permute(int field, int repr, void *states, uint64_t count, cudaStream_t stream, uint64_t *launches);
 

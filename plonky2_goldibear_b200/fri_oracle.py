@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _lib
 from .fields import Field, INPUT_COEFFS, INPUT_VALUES, REPR_CANONICAL
-from .merkle_tree import MerkleCap, MerkleTree, log2_strict, node_slot
+from .merkle_tree import DeviceMerkleTree, MerkleCap, MerkleTree, log2_strict, node_slot
 
 SALT_SIZE = 4  # oracle.rs:25
 
@@ -76,7 +76,8 @@ class PolynomialBatch:
     @classmethod
     def _commit(cls, field, columns, input_kind, rate_bits, blinding, cap_height, timing, ctx=None,
                 repr: int = REPR_CANONICAL, salts: Optional[Sequence[np.ndarray]] = None, rng=None,
-                shard_index: int = 0, shard_count: int = 0, want_leaves: bool = True, pinned_out: bool = False):
+                shard_index: int = 0, shard_count: int = 0, want_leaves: bool = True, pinned_out: bool = False,
+                keep_on_device: bool = False):
         ctx = ctx or _lib.default_context()
         if len(columns) == 0:
             raise IndexError("index out of bounds: the len is 0 but the index is 0")  # polynomials[0], oracle.rs:101
@@ -104,11 +105,13 @@ class PolynomialBatch:
         cap_local = max(cap_height - lg, 0)
         d = field.num_hash_out_elts
         alloc = ctx.pinned_empty if pinned_out else (lambda shape, dtype: np.empty(shape, dtype=dtype))
+        if keep_on_device:
+            want_leaves = False
         leaves = alloc((rows, width), field.dtype) if want_leaves else None
-        digests = alloc((max(2 * (rows - (1 << cap_local)), 0), d), field.dtype)
+        digests = None if keep_on_device else alloc((max(2 * (rows - (1 << cap_local)), 0), d), field.dtype)
         cap = np.empty((1 << cap_local, d), dtype=field.dtype)
         coeffs = None
-        if input_kind == INPUT_VALUES:
+        if input_kind == INPUT_VALUES and not keep_on_device:
             coeffs = [np.empty(degree, dtype=field.dtype) for _ in cols]
 
         desc = _lib.CommitDesc()
@@ -116,6 +119,10 @@ class PolynomialBatch:
         desc.log_n, desc.num_cols, desc.rate_bits, desc.cap_height = degree_log, len(cols), rate_bits, cap_height
         desc.num_salt_cols = len(salt_cols)
         desc.flags = 0 if want_leaves else _lib.FLAG_NO_LEAVES_OUT
+        handle = ctypes.c_void_p()
+        if keep_on_device:
+            desc.flags = _lib.FLAG_KEEP_ON_DEVICE
+            desc.batch_out = ctypes.pointer(handle)
         col_ptrs = _ptr_array(cols)
         desc.col_ptrs = ctypes.cast(col_ptrs, ctypes.POINTER(ctypes.c_void_p))
         if salt_cols:
@@ -126,7 +133,7 @@ class PolynomialBatch:
             desc.coeffs_out = ctypes.cast(out_ptrs, ctypes.POINTER(ctypes.c_void_p))
         desc.leaves_out = leaves.ctypes.data if leaves is not None else None
         desc.leaf_pitch = width
-        desc.digests_out = digests.ctypes.data if digests.size else None
+        desc.digests_out = digests.ctypes.data if digests is not None and digests.size else None
         desc.cap_out = cap.ctypes.data
         desc.shard_index, desc.shard_count = shard_index, shard_count
         t0 = time.perf_counter()
@@ -138,17 +145,30 @@ class PolynomialBatch:
                     continue
                 timing.record(name, s)
         polys = coeffs if coeffs is not None else cols
-        tree = MerkleTree(field, leaves, digests, MerkleCap(cap))
+        if keep_on_device:
+            tree = DeviceMerkleTree(field, ctx, handle, MerkleCap(cap))
+            polys = None if input_kind == INPUT_VALUES else cols  # coefficients stay on the device (download on demand)
+        else:
+            tree = MerkleTree(field, leaves, digests, MerkleCap(cap))
         batch = cls(field, polys, tree, degree_log, rate_bits, blinding)
         batch.desc = desc
         batch.wall_seconds = wall
         return batch
 
+    def download_polynomials(self) -> np.ndarray:
+        """coefficients [num_cols][n] of a device-resident batch"""
+        tree = self.merkle_tree
+        n = 1 << self.degree_log
+        cols = tree.leaf_len - (SALT_SIZE if self.blinding else 0)
+        out = np.empty((cols, n), dtype=self.field.dtype)
+        tree.ctx.check(tree.ctx.lib.p2g_batch_download(tree.ctx.handle, tree.handle, 3, out.ctypes.data))
+        return out
+
     # ------------------------------------------------------------------------------------------
     def get_lde_values(self, index: int, step: int) -> np.ndarray:
         """oracle.rs:153-158"""
         index = reverse_bits(index * step, self.degree_log + self.rate_bits)
-        row = self.merkle_tree.leaves[index]
+        row = self.merkle_tree.get(index)
         return row[: len(row) - (SALT_SIZE if self.blinding else 0)]
 
 

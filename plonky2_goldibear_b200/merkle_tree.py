@@ -87,6 +87,57 @@ class MerkleTree:
         return np.array(siblings, dtype=self.field.dtype).reshape(num_layers, self.field.num_hash_out_elts)
 
 
+class DeviceMerkleTree:
+    """The same tree with leaves and digests left in GPU memory (P2G_FLAG_KEEP_ON_DEVICE): `get` / `prove` are served
+    by gather kernels (p2g_batch_get_rows / p2g_batch_prove), only the cap lives on the host.  SURVEY.md 8f, N2."""
+
+    def __init__(self, field: Field, ctx, handle, cap: MerkleCap):
+        self.field, self.ctx, self.handle, self.cap = field, ctx, handle, cap
+        rows, width, layers, ncap = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_uint64()
+        ctx.check(ctx.lib.p2g_batch_shape(handle, ctypes.byref(rows), ctypes.byref(width), ctypes.byref(layers), ctypes.byref(ncap)))
+        self.num_leaves, self.leaf_len, self.num_layers = rows.value, width.value, layers.value
+
+    def get_many(self, indices) -> np.ndarray:
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64))
+        out = np.empty((idx.size, self.leaf_len), dtype=self.field.dtype)
+        self.ctx.check(self.ctx.lib.p2g_batch_get_rows(self.ctx.handle, self.handle, idx.ctypes.data, idx.size, out.ctypes.data))
+        return out
+
+    def get(self, i: int) -> np.ndarray:
+        return self.get_many([i])[0]
+
+    def prove_many(self, indices) -> np.ndarray:
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64))
+        out = np.empty((idx.size, self.num_layers, self.field.num_hash_out_elts), dtype=self.field.dtype)
+        self.ctx.check(self.ctx.lib.p2g_batch_prove(self.ctx.handle, self.handle, idx.ctypes.data, idx.size,
+                                                    out.ctypes.data if out.size else None))
+        return out
+
+    def prove(self, leaf_index: int) -> np.ndarray:
+        return self.prove_many([leaf_index])[0]
+
+    def download(self, what: str) -> np.ndarray:
+        """whole array back to the host: 'leaves' | 'digests' | 'cap'"""
+        d = self.field.num_hash_out_elts
+        shape = {"leaves": (self.num_leaves, self.leaf_len), "digests": (2 * (self.num_leaves - len(self.cap)), d),
+                 "cap": (len(self.cap), d)}[what]
+        out = np.empty(shape, dtype=self.field.dtype)
+        self.ctx.check(self.ctx.lib.p2g_batch_download(self.ctx.handle, self.handle, {"leaves": 0, "digests": 1, "cap": 2}[what],
+                                                       out.ctypes.data))
+        return out
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.p2g_batch_free(self.ctx.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def node_slot(layer: int, j: int) -> int:
     """Index, inside one cap subtree's digest block, of node j of `layer` (0 = leaf digests)."""
     return ((j >> 1) << (layer + 2)) + (2 << layer) - 2 + (j & 1)

@@ -373,3 +373,35 @@ def test_three_pass_ntt_plan(ctx, oracle):
         assert (np.stack(batch.polynomials) == ref["coeffs"]).all()
         assert (batch.merkle_tree.leaves == ref["leaves"]).all()
         assert (batch.merkle_tree.cap.hashes == ref["cap"]).all() and (batch.merkle_tree.digests == ref["digests"]).all()
+
+
+# ---- device-resident batch: get / prove / get_lde_values served from GPU memory ---------------------
+@pytest.mark.parametrize("field,log_n,c,r,h,blinding,kind", [(0, 12, 135, 3, 4, False, "values"), (0, 10, 20, 3, 4, True, "coeffs"),
+                                                            (1, 11, 167, 3, 4, False, "values"), (0, 1, 3, 3, 4, False, "values")])
+def test_device_resident_batch_accessors(ctx, oracle, field, log_n, c, r, h, blinding, kind):
+    import plonky2_goldibear_b200 as p2g
+    F = fields()[field]
+    n, N = 1 << log_n, 1 << (log_n + r)
+    vals = synthetic_columns(F.order, F.dtype, c, n)
+    salts = synthetic_columns(F.order, F.dtype, 4, N, seed=7) if blinding else None
+    ref = oracle.commit(field, vals, oracle.VALUES if kind == "values" else oracle.COEFFS, r, h, salts=salts)
+    fn = p2g.PolynomialBatch.from_values if kind == "values" else p2g.PolynomialBatch.from_coeffs
+    batch = fn(F, list(vals), r, blinding, h, ctx=ctx, salts=salts, keep_on_device=True)
+    tree = batch.merkle_tree
+    assert (tree.cap.hashes == ref["cap"]).all()
+    rng = np.random.default_rng(1)
+    idx = [0, N - 1] + [int(x) for x in rng.integers(0, N, size=20)]
+    assert (tree.get_many(idx) == ref["leaves"][idx]).all()
+    proofs = tree.prove_many(idx)
+    for i, k in enumerate(idx):
+        assert (proofs[i] == oracle.merkle_prove(field, ref["digests"], N, h, k)).all()
+        assert oracle.verify_merkle_proof_to_cap(field, ref["leaves"][k], k, ref["cap"], proofs[i])
+    lib = oracle.load()
+    for i in (0, 5 % N, N - 1):
+        assert (batch.get_lde_values(i, 1) == ref["leaves"][lib.p2o_reverse_bits(i, log_n + r)][:c]).all()
+    assert (tree.download("leaves") == ref["leaves"]).all()
+    assert (tree.download("digests") == ref["digests"]).all()
+    assert (batch.download_polynomials() == ref["coeffs"]).all()
+    with pytest.raises(p2g.P2GError):
+        tree.get(N)  # out of range, like the reference's slice index panic
+    tree.free()
