@@ -24,13 +24,17 @@
  * (telosnetwork/Plonky3, branch goldilocks_improvements, no lockfile); there is no Rust toolchain in the
  * build image, so the reference itself cannot be compiled (no oracle/_ref).  PARITY PINNING:
  *   pinned  : Poseidon-GL permutation (4 literal KATs), bit reversal (literal 256 table),
- *             GL sponge + 2-to-1 compression + Merkle path/cap convention (Merkle paths extracted from the
+ *             GL sponge + 2-to-1 compression + Merkle path/cap convention (196 Merkle paths extracted from the
  *             reference's golden proof bytes, recursion/regression_test_data.rs:93, tests/golden/),
- *             GL generator 7 (k_is in the golden common data).
+ *             GL generator 7, the GL two-adic root chain up to order 2^17, the coset shift and the bit-reversed leaf
+ *             order of from_values: the golden proof's Fiat-Shamir transcript and all 28 FRI query rounds re-verify
+ *             with this oracle's permutation and constants (tools/gl_fri_check.py, tests/test_golden_fri.py), and
+ *             fail with any other shift / root / leaf order.
  *   unpinned: Poseidon2-BabyBear numeric output (no literal vector exists in the reference tree; only the
  *             structure is pinned by the in-tree restatement), BabyBear generator 31 and two-adic root
- *             0x1a427a41, Goldilocks two-adic root 1753635133440165772 (upstream Plonky3 values;
- *             checked for order / 7-power consistency only).  => BabyBear parity is "parity unpinned".
+ *             0x1a427a41, Goldilocks two-adic roots of order above 2^17 (the 2^32 root 1753635133440165772 is the
+ *             upstream Plonky3 value = 7^((p-1)/2^32); the golden proof fixes its 2^15-th power).
+ *             => BabyBear parity is "parity unpinned"; Goldilocks parity is pinned.
  *
  * Element conventions: Goldilocks elements are uint64_t, BabyBear elements are uint32_t; both canonical
  * (< p) on input and output.  A digest is 32 bytes: 4 GL elements or 8 BB elements.
