@@ -148,6 +148,7 @@ def workload_config(args, field_name):
                 name, args.log_n, args.cols, args.rate_bits, args.cap_height),
             "field": field_name, "log_rows": args.log_n, "cols": args.cols, "rate_bits": args.rate_bits,
             "cap_height": args.cap_height, "parallelism": "coset-sharded x%d" % args.gpus if args.gpus > 1 else "single GPU",
+            "exchange": (args.exchange if args.gpus > 1 else None),
             "l2": "inputs (%.2f GB) and leaves (%.2f GB) are larger than the 126 MB L2; no flush needed" % (
                 args.cols * (1 << args.log_n) * (8 if field_name == "gl" else 4) / 1e9,
                 args.cols * ((1 << args.rate_bits) << args.log_n) * (8 if field_name == "gl" else 4) / 1e9)}
@@ -233,15 +234,83 @@ def run_ours(args, field_name):
     dev_desc.digests_out, dev_desc.cap_out = d_digests.data_ptr(), d_cap.data_ptr()
     kernel_s = np.zeros(4)
 
+    # ---- multi-GPU exchange.  Every rank needs all coefficient columns before its coset LDE.  "fused": the inverse NTT's
+    # last pass stores its columns straight into every rank's gather buffer over NVLink (CUDA-IPC mapped peer memory,
+    # p2g_intt_allgather) and a one-element all-reduce on the same stream is the only collective; two gather buffers
+    # alternate so that a fast rank never overwrites coefficients a slow rank is still reading.  "nccl": inverse NTT into
+    # a local slice, then ncclAllGather.
+    exchange = args.exchange if G > 1 else "none"
+    gather_ptrs, peer_tables, flag = [], [], None
+    if exchange == "fused":
+        try:
+            nbytes = G * cpr * n * es
+            handles = []
+            for k in range(2):
+                ptr = ctx.lib.p2g_dev_alloc(ctx.handle, nbytes)
+                if not ptr:
+                    raise RuntimeError("p2g_dev_alloc failed")
+                gather_ptrs.append(ptr)
+                hbuf = ctypes.create_string_buffer(64)
+                ctx.check(ctx.lib.p2g_ipc_export(ctx.handle, ptr, hbuf))
+                handles.append(hbuf.raw)
+            all_handles = [None] * G
+            dist.all_gather_object(all_handles, handles)
+            for k in range(2):
+                order = [gather_ptrs[k]]
+                for rr in range(G):
+                    if rr == rank:
+                        continue
+                    peer = ctypes.c_void_p()
+                    ctx.check(ctx.lib.p2g_ipc_import(ctx.handle, all_handles[rr][k], ctypes.byref(peer)))
+                    order.append(peer.value)
+                tbl = (ctypes.c_void_p * G)(*order)
+                keep.append(tbl)
+                peer_tables.append(tbl)
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        except Exception as e:  # e.g. IPC not permitted in this container: fall back to the NCCL all-gather
+            log("fused exchange unavailable (%s); using ncclAllGather" % e)
+            exchange = "nccl"
+        ok = torch.tensor([1 if exchange == "fused" else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0:
+            exchange = "nccl"
+    step_no = [0]
+
+    def exchange_coeffs(d2h_slice=None):
+        """inverse NTT of this rank's columns + all-gather; returns the device pointer holding all coefficients"""
+        if exchange == "fused":
+            k = step_no[0] & 1
+            step_no[0] += 1
+            ctx.check(ctx.lib.p2g_intt_allgather(ctx.handle, F.field_id, 0, L, cpr, rank * cpr, d_vals.data_ptr(),
+                                                 peer_tables[k], G))
+            with torch.cuda.stream(stream):
+                if d2h_slice is not None:
+                    own = gather_ptrs[k] + rank * cpr * n * es
+                    ctypes_copy_async(d2h_slice, own, (col1 - col0) * n * es)
+                dist.all_reduce(flag)  # cross-GPU barrier ordered on the library's stream
+            return gather_ptrs[k]
+        ctx.check(ctx.lib.p2g_transform(ctx.handle, F.field_id, 0, 0, L, cpr, 0,
+                                        _lib.FLAG_DEVICE_INPUT | _lib.FLAG_DEVICE_OUTPUT,
+                                        d_vals.data_ptr(), d_coeff_slice.data_ptr()))
+        with torch.cuda.stream(stream):
+            if d2h_slice is not None:
+                ctypes_copy_async(d2h_slice, d_coeff_slice.data_ptr(), (col1 - col0) * n * es)
+            dist.all_gather_into_tensor(d_coeffs, d_coeff_slice)
+        stream.synchronize()
+        return d_coeffs.data_ptr()
+
+    def ctypes_copy_async(host_arr, dev_ptr, nbytes):
+        # D2H of this rank's coefficient slice into pinned memory, on the library's stream
+        if nbytes:
+            ctx.check(ctx.lib.p2g_memcpy_async(ctx.handle, host_arr.ctypes.data, dev_ptr, nbytes, 1))
+
+    coeff_tbl = (ctypes.c_void_p * 1)()
+    keep.append(coeff_tbl)
+
     def device_step():
         if G > 1:
-            # column-sharded inverse NTT, then every rank needs all coefficient columns: one NVLink all-gather
-            ctx.check(ctx.lib.p2g_transform(ctx.handle, F.field_id, 0, 0, L, cpr, 0,
-                                            _lib.FLAG_DEVICE_INPUT | _lib.FLAG_DEVICE_OUTPUT,
-                                            d_vals.data_ptr(), d_coeff_slice.data_ptr()))
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(d_coeffs, d_coeff_slice)
-            stream.synchronize()
+            coeff_tbl[0] = exchange_coeffs()
+            dev_desc.col_ptrs = ctypes.cast(coeff_tbl, ctypes.POINTER(ctypes.c_void_p))
         ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(dev_desc)))
         kernel_s[:] += np.array(list(dev_desc.kernel_seconds))
 
@@ -306,13 +375,8 @@ def run_ours(args, field_name):
             if G > 1:
                 with torch.cuda.stream(stream):
                     d_vals[:col1 - col0].copy_(t_in[:col1 - col0], non_blocking=True)       # H2D of this rank's columns
-                ctx.check(ctx.lib.p2g_transform(ctx.handle, F.field_id, 0, 0, L, cpr, 0,
-                                                _lib.FLAG_DEVICE_INPUT | _lib.FLAG_DEVICE_OUTPUT,
-                                                d_vals.data_ptr(), d_coeff_slice.data_ptr()))
-                with torch.cuda.stream(stream):
-                    t_hc[:col1 - col0].copy_(d_coeff_slice[:col1 - col0], non_blocking=True)  # D2H of its coefficients
-                    dist.all_gather_into_tensor(d_coeffs, d_coeff_slice)
-                stream.synchronize()
+                coeff_tbl[0] = exchange_coeffs(d2h_slice=h_coeffs)                          # + D2H of its coefficients
+                e_desc.col_ptrs = ctypes.cast(coeff_tbl, ctypes.POINTER(ctypes.c_void_p))
             ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(e_desc)))
 
         e2e_step()
@@ -462,6 +526,9 @@ def main():
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="multi-GPU coefficient exchange: inverse NTT with the all-gather fused into its epilogue over "
+                         "peer memory (default), or a separate ncclAllGather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-log-n", type=int, default=16)
     args = ap.parse_args()

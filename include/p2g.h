@@ -168,6 +168,24 @@ int32_t p2g_permute(p2g_ctx *ctx, int32_t hash, int32_t repr, void *states, uint
 int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, uint32_t log_n, uint32_t num_cols,
                       uint32_t rate_bits, uint32_t flags, const void *in, void *out);
 
+/* ---- multi-GPU plumbing (one process per GPU).
+ * p2g_dev_alloc / p2g_ipc_export / p2g_ipc_import: a device buffer that the other ranks map over NVLink (CUDA IPC).
+ * p2g_intt_allgather: the column-sharded inverse NTT of `num_cols` columns (device pointer `values_dev`, column-major)
+ * whose last pass writes the coefficients at column `col_offset` of EVERY gather buffer: gather_bufs[0] is this rank's
+ * own [total_cols][n] buffer, gather_bufs[1..] the peers' (imported) ones.  The all-gather that every rank needs before
+ * its coset LDE is thereby fused into the transform's epilogue (stores to peer memory) instead of a separate NCCL call.
+ * Asynchronous on the context's stream; the caller puts a cross-GPU barrier between this call and the commit that
+ * reads the gathered coefficients (bench.py: a one-element all-reduce on the same stream, double-buffered). */
+void *p2g_dev_alloc(p2g_ctx *ctx, size_t bytes);
+void p2g_dev_free(p2g_ctx *ctx, void *ptr);
+int32_t p2g_ipc_export(p2g_ctx *ctx, void *dev_ptr, uint8_t handle_out[64]);
+int32_t p2g_ipc_import(p2g_ctx *ctx, const uint8_t handle[64], void **dev_ptr_out);
+int32_t p2g_ipc_close(p2g_ctx *ctx, void *dev_ptr);
+/* copy ordered on the context's stream: kind 0 = host->device, 1 = device->host, 2 = device->device */
+int32_t p2g_memcpy_async(p2g_ctx *ctx, void *dst, const void *src, size_t bytes, int32_t kind);
+int32_t p2g_intt_allgather(p2g_ctx *ctx, int32_t field, int32_t repr, uint32_t log_n, uint32_t num_cols, uint32_t col_offset,
+                           const void *values_dev, void *const *gather_bufs, uint32_t num_bufs);
+
 /* Device workspace currently held by the context (bytes) and a way to drop it. */
 uint64_t p2g_workspace_bytes(p2g_ctx *ctx);
 void p2g_release_workspace(p2g_ctx *ctx);

@@ -49,7 +49,8 @@ EXPORTS = [
     "p2g_abi_version", "p2g_init", "p2g_destroy", "p2g_last_error", "p2g_host_alloc", "p2g_host_free", "p2g_commit",
     "p2g_merkle", "p2g_merkle_finish_cap", "p2g_permute", "p2g_transform", "p2g_workspace_bytes",
     "p2g_release_workspace", "p2g_stream", "p2g_kernel_launches", "p2g_batch_get_rows", "p2g_batch_prove",
-    "p2g_batch_download", "p2g_batch_shape", "p2g_batch_free",
+    "p2g_batch_download", "p2g_batch_shape", "p2g_batch_free", "p2g_dev_alloc", "p2g_dev_free", "p2g_ipc_export",
+    "p2g_ipc_import", "p2g_ipc_close", "p2g_intt_allgather", "p2g_memcpy_async",
 ]
 
 
@@ -109,6 +110,20 @@ def load_library() -> ctypes.CDLL:
         lib.p2g_batch_shape.restype = i32
         lib.p2g_batch_free.argtypes = [vp, vp]
         lib.p2g_batch_free.restype = None
+        lib.p2g_dev_alloc.argtypes = [vp, ctypes.c_size_t]
+        lib.p2g_dev_alloc.restype = vp
+        lib.p2g_dev_free.argtypes = [vp, vp]
+        lib.p2g_dev_free.restype = None
+        lib.p2g_ipc_export.argtypes = [vp, vp, ctypes.c_char_p]
+        lib.p2g_ipc_export.restype = i32
+        lib.p2g_ipc_import.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
+        lib.p2g_ipc_import.restype = i32
+        lib.p2g_ipc_close.argtypes = [vp, vp]
+        lib.p2g_ipc_close.restype = i32
+        lib.p2g_intt_allgather.argtypes = [vp, i32, i32, u32, u32, u32, vp, ctypes.POINTER(vp), u32]
+        lib.p2g_intt_allgather.restype = i32
+        lib.p2g_memcpy_async.argtypes = [vp, vp, vp, ctypes.c_size_t, i32]
+        lib.p2g_memcpy_async.restype = i32
         _LIB = lib
         return lib
 

@@ -305,7 +305,10 @@ __global__ void __launch_bounds__(256, 3) ntt_final_natural_kernel(NttPass p) {
         E v = x[w * S + pp];
         if (p.use_final_scale) v = F::mul(v, fs);
         if (p.out_user_repr) v = F::store_user(v);
-        dst[(size_t)(d0 + w) + ((size_t)f << lc)] = v;
+        const size_t o = (size_t)(d0 + w) + ((size_t)f << lc);
+        dst[o] = v;
+        // fused all-gather: the same 64-byte run goes to every peer's buffer (plain stores to NVLink-mapped memory)
+        for (u32 k = 0; k < p.num_peers; k++) ((E *)p.peer_dst[k] + (size_t)col * p.dst_col_stride)[o] = v;
     }
 }
 

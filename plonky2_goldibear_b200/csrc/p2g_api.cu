@@ -294,7 +294,8 @@ void plan_passes(unsigned log_n, unsigned lps[3], unsigned *num) {
 //            leaf matrix `dst` starting at row_base.
 // `src` is overwritten when inverse (the strided passes run in place); forward uses `tmp` for the strided passes.
 int run_transform(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsigned log_n, unsigned num_cols,
-                  void *src, void *tmp, void *dst, uint64_t dst_stride, uint64_t shift, uint64_t row_base) {
+                  void *src, void *tmp, void *dst, uint64_t dst_stride, uint64_t shift, uint64_t row_base,
+                  void *const *peer_dst = nullptr, unsigned num_peers = 0) {
     unsigned lps[3], P;
     plan_passes(log_n, lps, &P);
     const uint64_t n = (uint64_t)1 << log_n;
@@ -337,6 +338,8 @@ int run_transform(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsi
             p.dst_col_stride = dst_stride;
             p.out_user_repr = 1;
             if (inverse) {
+                for (unsigned k = 0; k < num_peers && k < 8; k++) p.peer_dst[k] = peer_dst[k];
+                p.num_peers = num_peers;
                 p.use_final_scale = 1;
                 p.final_scale = f_internal(f, f_pow(f, f_inv(f, 2), log_n));  // n^-1 = (1/2)^lg n, fft.rs:78
                 launch_ntt_pass(f.id, repr, NTT_FINAL_NATURAL, p, ctx->stream, &ctx->launches);
@@ -1014,6 +1017,82 @@ int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, u
         return ctx->fail(P2G_ERR_INVALID, "unknown transform kind %d", kind);
     }
     CK(cudaStreamSynchronize(st));
+    return P2G_OK;
+}
+
+// ---- multi-GPU plumbing: device buffers that other processes can map, and the fused inverse-NTT + all-gather --------
+void *p2g_dev_alloc(p2g_ctx *ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->fail(P2G_ERR_OOM, "cudaMalloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void p2g_dev_free(p2g_ctx *ctx, void *ptr) {
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (ptr) cudaFree(ptr);
+}
+int32_t p2g_ipc_export(p2g_ctx *ctx, void *dev_ptr, uint8_t handle_out[64]) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle_out, &h, 64);
+    return P2G_OK;
+}
+int32_t p2g_ipc_import(p2g_ctx *ctx, const uint8_t handle[64], void **dev_ptr_out) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return P2G_OK;
+}
+int32_t p2g_ipc_close(p2g_ctx *ctx, void *dev_ptr) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaIpcCloseMemHandle(dev_ptr));
+    return P2G_OK;
+}
+
+int32_t p2g_memcpy_async(p2g_ctx *ctx, void *dst, const void *src, size_t bytes, int32_t kind) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    CK(cudaMemcpyAsync(dst, src, bytes, k, ctx->stream));
+    return P2G_OK;
+}
+
+int32_t p2g_intt_allgather(p2g_ctx *ctx, int32_t field, int32_t repr, uint32_t log_n, uint32_t num_cols, uint32_t col_offset,
+                           const void *values_dev, void *const *gather_bufs, uint32_t num_bufs) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (field != P2G_FIELD_GOLDILOCKS && field != P2G_FIELD_BABYBEAR) return ctx->fail(P2G_ERR_UNSUPPORTED, "unknown field");
+    const FieldInfo &f = field == P2G_FIELD_GOLDILOCKS ? kGl : kBb;
+    if (f.id == FIELD_GL) repr = 0;
+    if (!num_cols || !values_dev || !gather_bufs || num_bufs == 0 || num_bufs > 9) return ctx->fail(P2G_ERR_INVALID, "bad arguments");
+    if (log_n > f.two_adicity || log_n > 3 * MAX_TILE_LOG) return ctx->fail(P2G_ERR_INVALID, "transform size unsupported");
+    const uint64_t n = (uint64_t)1 << log_n;
+    const size_t bytes = (size_t)num_cols * n * f.elem;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in, bytes))) return rc;
+    // the strided passes run in place: work on a copy so that the caller's values survive
+    CK(cudaMemcpyAsync(ctx->in.ptr, values_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    void *peers[8];
+    for (unsigned k = 1; k < num_bufs; k++) peers[k - 1] = (char *)gather_bufs[k] + (size_t)col_offset * n * f.elem;
+    void *own = (char *)gather_bufs[0] + (size_t)col_offset * n * f.elem;
+    if ((rc = run_transform(ctx, f, repr, true, log_n, num_cols, ctx->in.ptr, nullptr, own, n, 0, 0, peers, num_bufs - 1))) return rc;
+    // asynchronous on the context's stream: the caller orders the cross-GPU barrier and the commit behind it
     return P2G_OK;
 }
 

@@ -59,6 +59,10 @@ struct NttPass {
     uint64_t final_scale;  // internal representation; multiplied into the outputs of a final pass when use_final_scale
     uint32_t use_final_scale;
     uint64_t row_base;     // leaf output: first row of this coset
+    // final natural pass of a column-sharded inverse transform: the coefficients are also written into the gather
+    // buffers of the other GPUs (peer pointers mapped over NVLink), i.e. the all-gather is fused into the epilogue
+    void *peer_dst[8];
+    uint32_t num_peers;
     uint32_t async_ok;       // src base and column stride are 16-byte aligned: the tile may be staged with cp.async
     uint32_t in_user_repr;   // 1: src is in the caller's representation (load conversion), 0: internal
     uint32_t out_user_repr;  // 1: dst is in the caller's representation (canonical / chosen repr)

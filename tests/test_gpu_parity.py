@@ -405,3 +405,33 @@ def test_device_resident_batch_accessors(ctx, oracle, field, log_n, c, r, h, bli
     with pytest.raises(p2g.P2GError):
         tree.get(N)  # out of range, like the reference's slice index panic
     tree.free()
+
+
+def test_fused_intt_allgather_emulated_on_one_gpu(ctx, oracle):
+    """The fused inverse-NTT + all-gather (p2g_intt_allgather) with both 'ranks' on one GPU: each rank transforms its
+    column share and its epilogue writes the coefficients into BOTH gather buffers; afterwards every buffer holds every
+    column, bit-identical to the oracle's ifft.  (Across GPUs the peer buffers are CUDA-IPC mappings; bench.py --gpus N.)"""
+    import ctypes
+    import torch
+    for field, log_n, c in ((0, 12, 7), (1, 13, 10), (0, 5, 3)):
+        F = fields()[field]
+        n = 1 << log_n
+        world, cpr = 2, (c + 1) // 2
+        vals = synthetic_columns(F.order, F.dtype, c, n, seed=21)
+        tdt = torch.int64 if field == 0 else torch.int32
+        bufs = [torch.zeros((world * cpr, n), dtype=tdt, device="cuda") for _ in range(world)]
+        torch.cuda.synchronize()
+        for rank in range(world):
+            c0, c1 = rank * cpr, min((rank + 1) * cpr, c)
+            share = torch.from_numpy(np.ascontiguousarray(vals[c0:c1]).view(np.int64 if field == 0 else np.int32)).cuda()
+            torch.cuda.synchronize()
+            order = [bufs[rank]] + [bufs[r] for r in range(world) if r != rank]
+            ptrs = (ctypes.c_void_p * world)(*[b.data_ptr() for b in order])
+            ctx.check(ctx.lib.p2g_intt_allgather(ctx.handle, field, 0, log_n, c1 - c0, c0, share.data_ptr(), ptrs, world))
+        torch.cuda.synchronize()
+        stream = torch.cuda.ExternalStream(ctx.lib.p2g_stream(ctx.handle))
+        stream.synchronize()
+        exp = np.stack([oracle.ifft(field, v) for v in vals])
+        for b in bufs:
+            got = b.cpu().numpy().view(F.dtype)[:c]
+            assert (got == exp).all()
