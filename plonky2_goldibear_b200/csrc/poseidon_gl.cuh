@@ -46,33 +46,77 @@ __device__ __forceinline__ u64 pgl_fold(u64 acc_lo, u64 acc_hi) {
     return gl_pack(w0, w1);
 }
 
+// Circulant part of the MDS layer on one 32-bit half of the state: y[r] = sum_i circ[i] * x[(i + r) % 12] with
+// circ = (17,15,41,16,2,28,13,13,39,18,34,20) (poseidon_goldilocks.rs:301), computed WITHOUT multiplications.
+// IMAD.WIDE costs 3.6 issue cycles on B200 and the direct product needs 144 of them per half; instead the length-12
+// cyclic correlation is split as 12 = 3 x 4: a 4-point DFT along t of x[j + 3t] (integers and Gaussian integers,
+// adds only), three 3-point "twisted" cyclic products modulo z^3 - lambda (lambda = 1, i, -1; the fourth is the
+// conjugate of the second because the input is real) against the transformed circulant, and the inverse 4-point DFT.
+// The transformed circulant, with the 1/4 (and 1/2 for the complex pair) of the inverse folded in, is all small:
+//   f=0: (16, 32, 16)   f=2: (-1, -8, 2)   f=1: (2+i, -4-i, 16-i)
+// so every product is a shift, an add or a negation on 64-bit signed integers (values stay below 2^42).
+// The reference reaches the same product through winterfell's mds_multiply_freq (:956-1088); this derivation and its
+// constants were re-done from the circulant and checked against the direct product (tests: Poseidon known answers).
+__device__ __forceinline__ void pgl_circ_half(const u32 x[12], long long y[12]) {
+    long long f0[3], f2[3], re[3], im[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        long long x0 = x[j], x1 = x[j + 3], x2 = x[j + 6], x3 = x[j + 9];
+        long long p02 = x0 + x2, p13 = x1 + x3;
+        f0[j] = p02 + p13;
+        f2[j] = p02 - p13;
+        re[j] = x0 - x2;
+        im[j] = x1 - x3;
+    }
+    // f = 0 (lambda = 1), constants (16, 32, 16):  Y0 = 16 * (s + a2, s + a0, s + a1)
+    long long s = f0[0] + f0[1] + f0[2];
+    long long y0[3] = {(s + f0[2]) << 4, (s + f0[0]) << 4, (s + f0[1]) << 4};
+    // f = 2 (lambda = -1), constants (-1, -8, 2)
+    long long y2[3] = {(f2[2] << 3) - f2[0] - (f2[1] << 1), -(f2[0] << 3) - f2[1] - (f2[2] << 1), (f2[0] << 1) - (f2[1] << 3) - f2[2]};
+    // f = 1 (lambda = i), constants b0 = 2+i, b1 = -4-i, b2 = 16-i;  a*(br + i*bi) = (r*br - i*bi) + i*(r*bi + i*br)
+    long long r0 = re[0], i0 = im[0], r1 = re[1], i1 = im[1], r2 = re[2], i2 = im[2];
+    // T = a1*b2 + a2*b1
+    long long t_re = (r1 << 4) + i1 - (r2 << 2) + i2;
+    long long t_im = (i1 << 4) - r1 - r2 - (i2 << 2);
+    long long y1r[3], y1i[3];
+    y1r[0] = (r0 << 1) - i0 - t_im;                       // a0*b0 + i*T
+    y1i[0] = r0 + (i0 << 1) + t_re;
+    y1r[1] = i0 - (r0 << 2) + (r1 << 1) - i1 + r2 - (i2 << 4);   // a0*b1 + a1*b0 + i*a2*b2
+    y1i[1] = r1 - r0 - (i0 << 2) + (i1 << 1) + (r2 << 4) + i2;
+    y1r[2] = (r0 << 4) + i0 - (r1 << 2) + i1 + (r2 << 1) - i2;   // a0*b2 + a1*b1 + a2*b0
+    y1i[2] = (i0 << 4) - r0 - r1 - (i1 << 2) + r2 + (i2 << 1);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        long long p = y0[j] + y2[j], m = y0[j] - y2[j];
+        y[j] = p + y1r[j];
+        y[j + 3] = m + y1i[j];
+        y[j + 6] = p - y1r[j];
+        y[j + 9] = m - y1i[j];
+    }
+}
+
 // out = MDS * s (+ next round constants).  MDS = circ(17,15,41,16,2,28,13,13,39,18,34,20) + diag(8,0,...)
 // (poseidon_goldilocks.rs:301-302; row r of the product is sum_i circ[i] * s[(i+r)%12], :547-557).
 template <bool ADD_CONST>
 __device__ __forceinline__ void pgl_mds(u64 s[12], const u64 *next_rc) {
-    const u32 circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
     u32 lo[12], hi[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         lo[i] = (u32)s[i];
         hi[i] = (u32)(s[i] >> 32);
     }
+    long long yl[12], yh[12];
+    pgl_circ_half(lo, yl);
+    pgl_circ_half(hi, yh);
+    yl[0] += (long long)lo[0] << 3;  // the diagonal entry 8
+    yh[0] += (long long)hi[0] << 3;
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        u64 al = 0, ah = 0;
+        u64 al = (u64)yl[r], ah = (u64)yh[r];
         if (ADD_CONST) {
             u64 c = next_rc[r];
-            al = (u32)c;
-            ah = c >> 32;
-        }
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            al += (u64)lo[(i + r) % 12] * circ[i];
-            ah += (u64)hi[(i + r) % 12] * circ[i];
-        }
-        if (r == 0) {
-            al += (u64)lo[0] * 8u;
-            ah += (u64)hi[0] * 8u;
+            al += (u32)c;
+            ah += c >> 32;
         }
         s[r] = pgl_fold(al, ah);
     }
