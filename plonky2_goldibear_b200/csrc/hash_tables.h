@@ -5,14 +5,7 @@
 namespace p2g {
 
 struct PoseidonGlTables {
-    unsigned long long pre_add[2][12];    // round constants of the first full round of each half (rounds 0 and 26)
-    unsigned long long mds_add[8][12];    // constants folded into the MDS of full round i: those of the NEXT layer
-                                          // (rounds 1,2,3, the partial rounds' first constants, rounds 27,28,29, zero);
-                                          // all from ALL_ROUND_CONSTANTS, poseidon_goldilocks.rs:114-212
-    unsigned long long k[22];             // added to s0 after its S-box in partial round r
-    unsigned long long row[22][11];       // d = 25*s0 + sum_i row[r][i] * s[i+1]
-    unsigned long long col[22][11];       // s[i+1] += s0 * col[r][i]
-    unsigned long long init[11][11];      // dense block applied to s[1..] before the first partial round
+    unsigned long long rc[31][12];  // rc[r] = ALL_ROUND_CONSTANTS[12r..12r+12] (poseidon_goldilocks.rs:114-212), rc[30] = 0
 };
 
 struct Poseidon2BbTables {

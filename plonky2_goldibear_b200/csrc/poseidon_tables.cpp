@@ -1,130 +1,13 @@
 // Host-side construction of the Poseidon / Poseidon2 constant tables uploaded to __constant__ memory.
-//
-// Goldilocks Poseidon: the reference ships the "fast partial round" tables as literals generated by an external
-// sage script (plonky2/src/hash/poseidon_goldilocks.rs:304-492).  They are a pure function of the round
-// constants (:114-212) and the MDS matrix (:301-302); we recompute them here:
-//   1. constants: walking the partial rounds backwards, the constant vector of round r is pulled through M^-1;
-//      its first entry becomes the scalar added to s0 after the S-box of round r-1, the rest joins round r-1.
-//   2. matrices: with A the matrix still owed after the S-box of round r (A = M for the last partial round),
-//      A = [[a00, a_row],[a_col, Ahat]] = S_r * diag(1, Ahat),  S_r = [[a00, a_row*Ahat^-1],[a_col, I]] sparse;
-//      diag(1, Ahat) commutes with the partial S-box and is merged into the previous round: A <- diag(1,Ahat)*M.
-//      What is left in front of round 0 is the dense (t-1)x(t-1) pre-matrix.
-// tests/ check fast == naive through the known-answer vectors.
-#include <cstdio>
-#include <cstdlib>
-#include <vector>
-
 #include "p2g_constants.h"
 #include "p2g_internal.h"
 
 namespace p2g {
 
-typedef std::vector<std::vector<u64>> Mat;
-typedef GlHost G;
-
-static Mat matmul(const Mat &a, const Mat &b) {
-    size_t n = a.size(), k = b.size(), m = b[0].size();
-    Mat c(n, std::vector<u64>(m, 0));
-    for (size_t i = 0; i < n; i++)
-        for (size_t t = 0; t < k; t++) {
-            if (!a[i][t]) continue;
-            for (size_t j = 0; j < m; j++) c[i][j] = G::add(c[i][j], G::mul(a[i][t], b[t][j]));
-        }
-    return c;
-}
-
-static Mat inverse(Mat a) {
-    size_t n = a.size();
-    Mat r(n, std::vector<u64>(n, 0));
-    for (size_t i = 0; i < n; i++) r[i][i] = 1;
-    for (size_t col = 0; col < n; col++) {
-        size_t piv = col;
-        while (piv < n && a[piv][col] == 0) piv++;
-        if (piv == n) {
-            fprintf(stderr, "p2g: singular matrix while deriving Poseidon tables\n");
-            abort();
-        }
-        a[piv].swap(a[col]);
-        r[piv].swap(r[col]);
-        u64 d = G::inv(a[col][col]);
-        for (size_t j = 0; j < n; j++) {
-            a[col][j] = G::mul(a[col][j], d);
-            r[col][j] = G::mul(r[col][j], d);
-        }
-        for (size_t i = 0; i < n; i++) {
-            u64 f = a[i][col];
-            if (i == col || f == 0) continue;
-            for (size_t j = 0; j < n; j++) {
-                a[i][j] = G::sub(a[i][j], G::mul(f, a[col][j]));
-                r[i][j] = G::sub(r[i][j], G::mul(f, r[col][j]));
-            }
-        }
-    }
-    return r;
-}
-
 void build_poseidon_gl_tables(PoseidonGlTables *T) {
-    const int W = 12, NP = 22, HF = 4;
-    u64 rc[30][12];
     for (int r = 0; r < 30; r++)
-        for (int i = 0; i < W; i++) rc[r][i] = P2G_GL_POSEIDON_RC[r * W + i] % G::P;
-    Mat M(W, std::vector<u64>(W));
-    for (int r = 0; r < W; r++)
-        for (int c = 0; c < W; c++) M[r][c] = P2G_GL_MDS_CIRC[(c - r + W) % W] + (r == c ? P2G_GL_MDS_DIAG[r] : 0);
-    Mat Minv = inverse(M);
-
-    std::vector<std::vector<u64>> cv(NP, std::vector<u64>(W));
-    for (int r = 0; r < NP; r++)
-        for (int i = 0; i < W; i++) cv[r][i] = rc[HF + r][i];
-    T->k[NP - 1] = 0;
-    for (int r = NP - 1; r >= 1; r--) {
-        for (int i = 0; i < W; i++) {
-            u64 e = 0;
-            for (int j = 0; j < W; j++) e = G::add(e, G::mul(Minv[i][j], cv[r][j]));
-            if (i == 0)
-                T->k[r - 1] = e;
-            else
-                cv[r - 1][i] = G::add(cv[r - 1][i], e);
-        }
-    }
-    for (int i = 0; i < W; i++) {
-        T->pre_add[0][i] = rc[0][i];
-        T->pre_add[1][i] = rc[HF + NP][i];
-        for (int r = 0; r < 3; r++) {
-            T->mds_add[r][i] = rc[r + 1][i];
-            T->mds_add[4 + r][i] = rc[HF + NP + r + 1][i];
-        }
-        T->mds_add[3][i] = cv[0][i];  // partial_first_constant_layer
-        T->mds_add[7][i] = 0;
-    }
-
-    Mat A = M;
-    for (int r = NP - 1; r >= 0; r--) {
-        Mat Ahat(W - 1, std::vector<u64>(W - 1));
-        for (int i = 1; i < W; i++)
-            for (int j = 1; j < W; j++) Ahat[i - 1][j - 1] = A[i][j];
-        Mat AhatInv = inverse(Ahat);
-        if (A[0][0] != 25) {
-            fprintf(stderr, "p2g: unexpected sparse-factor corner %llu\n", (unsigned long long)A[0][0]);
-            abort();
-        }
-        for (int j = 0; j < W - 1; j++) {
-            u64 e = 0;
-            for (int i = 0; i < W - 1; i++) e = G::add(e, G::mul(A[0][i + 1], AhatInv[i][j]));
-            T->row[r][j] = e;
-            T->col[r][j] = A[j + 1][0];
-        }
-        if (r == 0) {
-            for (int i = 0; i < W - 1; i++)
-                for (int j = 0; j < W - 1; j++) T->init[i][j] = Ahat[i][j];
-        } else {
-            Mat D(W, std::vector<u64>(W, 0));
-            D[0][0] = 1;
-            for (int i = 1; i < W; i++)
-                for (int j = 1; j < W; j++) D[i][j] = Ahat[i - 1][j - 1];
-            A = matmul(D, M);
-        }
-    }
+        for (int i = 0; i < 12; i++) T->rc[r][i] = P2G_GL_POSEIDON_RC[r * 12 + i] % GlHost::P;
+    for (int i = 0; i < 12; i++) T->rc[30][i] = 0;
 }
 
 void build_poseidon2_bb_tables(Poseidon2BbTables *T) {

@@ -7,7 +7,7 @@ typedef unsigned int u32;
 #define ITER 512
 
 template <int OP>
-__global__ void __launch_bounds__(256) probe(u32 *out, u32 seed, u32 m0, u32 m1) {
+__global__ void __launch_bounds__(256) probe(u32 *out, u32 seed, u32 m0, u32 m1, u32 m2) {
     u64 acc[8];
     u32 x[8], y[8];
 #pragma unroll
@@ -31,6 +31,14 @@ __global__ void __launch_bounds__(256) probe(u32 *out, u32 seed, u32 m0, u32 m1)
                 if (OP == 5) { acc[j] += (u64)x[(j + k) & 7] * (u32)(17 + 2 * k); y[j] += x[(j + k + 1) & 7]; }             // WIDE + IADD3
                 if (OP == 6) { y[j] += x[(j + k + 1) & 7]; }                                                                  // IADD3 only
                 if (OP == 7) { acc[j] += ((u64)x[(j + k) & 7] << 32) | y[(j + k) & 7]; }                                      // 64-bit add (IADD3 + IADD3.X)
+                if (OP == 9) { acc[j] += acc[(j + k + 1) & 7] ^ 0; }                                                           // 64-bit reg add (ptxas picks IADD3.X or IMAD.X)
+                if (OP == 10) {  // same with a third, opaque-zero operand on the high word: must be IADD3.X
+                    u32 al = (u32)acc[j], ah = (u32)(acc[j] >> 32), bl = (u32)acc[(j + k + 1) & 7], bh = (u32)(acc[(j + k + 1) & 7] >> 32);
+                    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(al), "+r"(ah) : "r"(bl), "r"(bh + m2));
+                    acc[j] = ((u64)ah << 32) | al;
+                }
+                if (OP == 11) { y[j] = x[(j + k + 1) & 7] - y[(j+k)&7]; }                                                      // 2-input sub (IADD3 or IMAD.IADD)
+                if (OP == 12) { y[j] = x[(j + k + 1) & 7] - y[(j+k)&7] + m2; }                                                 // 3-input (IADD3)
                 if (OP == 8) { acc[j] += (u64)x[(j + k) & 7] * (u32)(17 + 2 * k); acc[(j + 1) & 7] += ((u64)y[j] << 32) | x[j]; }  // WIDE + 64-bit add
             }
         }
@@ -53,10 +61,10 @@ void run(const char *name, double ops_per_inner) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    probe<OP><<<blocks, threads>>>(out, 12345, 0x9e3779b9u, 0x7f4a7c15u);
+    probe<OP><<<blocks, threads>>>(out, 12345, 0x9e3779b9u, 0x7f4a7c15u, 0u);
     cudaDeviceSynchronize();
     cudaEventRecord(e0);
-    probe<OP><<<blocks, threads>>>(out, 12345, 0x9e3779b9u, 0x7f4a7c15u);
+    probe<OP><<<blocks, threads>>>(out, 12345, 0x9e3779b9u, 0x7f4a7c15u, 0u);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
@@ -77,5 +85,9 @@ int main() {
     run<5>("IMAD.WIDE + IADD3", 2);
     run<4>("IMAD.WIDE + IADD3 + LOP3", 3);
     run<8>("IMAD.WIDE + add64", 3);
+    run<9>("add64 reg+reg (ptxas mix)", 2);
+    run<10>("add64 with opaque zero", 2);
+    run<11>("sub32 2-input", 1);
+    run<12>("sub32 3-input", 1);
     return 0;
 }
