@@ -464,7 +464,7 @@ def run_ours(args, field_name):
         int_pipe = {"kernel": "leaf_hash_kernel", "issue_cycles_per_warp_permutation": measured,
                     "model_cycles_per_warp_permutation": model[key]["cycles_per_warp_permutation"],
                     "issue_slot_utilisation_vs_model": model[key]["cycles_per_warp_permutation"] / measured,
-                    "model": "profiles/r1_leaf_sponge_cost_model.json (IMAD.WIDE/HI 3.6, IMAD 2, other 1 issue cycles; tools/microbench/imad_probe.cu)"}
+                    "model": "profiles/r1_leaf_sponge_cost_model.json (fitted on B200: 1.42 cycles per integer warp instruction, 2.59 per IMAD.WIDE/HI; tools/sass_cost.py)"}
     except Exception as e:  # the model file is evidence, not a dependency
         int_pipe = {"unavailable": str(e)}
     line = {

@@ -1,12 +1,12 @@
 // Poseidon over Goldilocks, width 12, x^7, 4 + 22 + 4 rounds -- one permutation per thread, state in registers.
 //
-// Replaces the reference's CPU permutation plonky2/src/hash/poseidon_goldilocks.rs:912-922 (full rounds :889-897,
-// fast partial rounds :899-909 with mds_partial_layer_init :657-683 and mds_partial_layer_fast :718-744).
+// Replaces the reference's CPU permutation plonky2/src/hash/poseidon_goldilocks.rs:912-922 (same function as its
+// plain form :927-948: constant layer :519-535, S-box :746-760, MDS :547-557).
 // Differences that do not change a single output bit:
-//   * the MDS layer multiplies 32-bit halves of the state by the small circulant constants with IMAD.WIDE and
-//     folds the NEXT round's constants into the accumulators (the reference adds them at the top of a round);
-//   * state words are kept as arbitrary u64 representatives and made canonical only when a digest is stored;
-//   * the sparse-factor tables are re-derived on the host at context creation (poseidon_tables.cpp), not pasted.
+//   * the MDS layer works on the 32-bit halves of the state with shifts and adds only (pgl_circ_half) and folds the
+//     NEXT round's constants into its sums (the reference adds them at the top of a round);
+//   * the partial rounds use the plain form (S-box on lane 0, full MDS) rather than the sparse-factor form;
+//   * state words are kept as arbitrary u64 representatives and made canonical only when a digest is stored.
 #pragma once
 #include "field_gl.cuh"
 #include "hash_tables.h"
@@ -48,7 +48,7 @@ __device__ __forceinline__ u64 pgl_fold(u64 acc_lo, u64 acc_hi) {
 
 // Circulant part of the MDS layer on one 32-bit half of the state: y[r] = sum_i circ[i] * x[(i + r) % 12] with
 // circ = (17,15,41,16,2,28,13,13,39,18,34,20) (poseidon_goldilocks.rs:301), computed WITHOUT multiplications.
-// IMAD.WIDE costs 3.6 issue cycles on B200 and the direct product needs 144 of them per half; instead the length-12
+// The direct product needs 144 IMAD.WIDE per half (2.6 issue cycles each on B200 against 1.4 for an add); instead the length-12
 // cyclic correlation is split as 12 = 3 x 4: a 4-point DFT along t of x[j + 3t] (integers and Gaussian integers,
 // adds only), three 3-point "twisted" cyclic products modulo z^3 - lambda (lambda = 1, i, -1; the fourth is the
 // conjugate of the second because the input is real) against the transformed circulant, and the inverse 4-point DFT.
@@ -57,7 +57,7 @@ __device__ __forceinline__ u64 pgl_fold(u64 acc_lo, u64 acc_hi) {
 // so every product is a shift, an add or a negation on 64-bit signed integers (values stay below 2^42).
 // The reference reaches the same product through winterfell's mds_multiply_freq (:956-1088); this derivation and its
 // constants were re-done from the circulant and checked against the direct product (tests: Poseidon known answers).
-__device__ __forceinline__ void pgl_circ_half(const u32 x[12], long long y[12]) {
+__device__ __forceinline__ void pgl_circ_half(const u32 x[12], long long y[12], const long long add[12]) {
     long long f0[3], f2[3], re[3], im[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -88,10 +88,10 @@ __device__ __forceinline__ void pgl_circ_half(const u32 x[12], long long y[12]) 
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         long long p = y0[j] + y2[j], m = y0[j] - y2[j];
-        y[j] = p + y1r[j];
-        y[j + 3] = m + y1i[j];
-        y[j + 6] = p - y1r[j];
-        y[j + 9] = m - y1i[j];
+        y[j] = p + y1r[j] + add[j];
+        y[j + 3] = m + y1i[j] + add[j + 3];
+        y[j + 6] = p - y1r[j] + add[j + 6];
+        y[j + 9] = m - y1i[j] + add[j + 9];
     }
 }
 
@@ -105,28 +105,26 @@ __device__ __forceinline__ void pgl_mds(u64 s[12], const u64 *next_rc) {
         lo[i] = (u32)s[i];
         hi[i] = (u32)(s[i] >> 32);
     }
-    long long yl[12], yh[12];
-    pgl_circ_half(lo, yl);
-    pgl_circ_half(hi, yh);
-    yl[0] += (long long)lo[0] << 3;  // the diagonal entry 8
-    yh[0] += (long long)hi[0] << 3;
+    long long yl[12], yh[12], cl[12], ch[12];
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        u64 al = (u64)yl[r], ah = (u64)yh[r];
-        if (ADD_CONST) {
-            u64 c = next_rc[r];
-            al += (u32)c;
-            ah += c >> 32;
-        }
-        s[r] = pgl_fold(al, ah);
+        u64 c = ADD_CONST ? next_rc[r] : 0;
+        cl[r] = (long long)(u32)c;
+        ch[r] = (long long)(c >> 32);
     }
+    cl[0] += (long long)lo[0] << 3;  // the diagonal entry 8
+    ch[0] += (long long)hi[0] << 3;
+    pgl_circ_half(lo, yl, cl);
+    pgl_circ_half(hi, yh, ch);
+#pragma unroll
+    for (int r = 0; r < 12; r++) s[r] = pgl_fold((u64)yl[r], (u64)yh[r]);
 }
 
 // Round structure (poseidon_goldilocks.rs:927-948, the reference's `poseidon_naive`): 30 rounds of
 // [add constants, S-box, MDS]; rounds 0-3 and 26-29 apply the S-box to all 12 lanes, rounds 4-25 to lane 0 only.
 // The reference's production form (:912-922) replaces the 22 partial rounds by a dense pre-matrix plus sparse
 // factors with 64-bit constants (23 full multiplications a round); with the multiplication-free MDS above the plain
-// form is cheaper on this machine (B200 issue model: ~550 cycles a partial round against ~760) and needs no derived
+// form is cheaper on this machine (measured per warp: S-box 122 + MDS 606 cycles a partial round against ~810, and no pre-matrix) and needs no derived
 // tables.  Both forms compute the same permutation (the oracle checks naive == fast, tests check this == oracle).
 //
 // Code-size discipline: the permutation is ~25k dynamic instructions, and a warp that strays from its neighbours

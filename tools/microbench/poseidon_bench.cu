@@ -31,6 +31,34 @@ __global__ void __launch_bounds__(BLOCK, MINB) gl_chain(const u64 *in, u64 *out,
 #pragma unroll
     for (int i = 0; i < 12; i++) out[t * 12 + i] = gl_canon(s[i]);
 }
+// component probes: 30 x (12 S-boxes) and 30 x MDS layers, same loop shape as the permutation
+__global__ void __launch_bounds__(BLOCK, MINB) gl_sbox_chain(const u64 *in, u64 *out, int chain) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = in[t * 12 + i];
+#pragma unroll 1
+    for (int k = 0; k < chain * 30; k++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = pgl_sbox(s[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) out[t * 12 + i] = gl_canon(s[i]);
+}
+__global__ void __launch_bounds__(BLOCK, MINB) gl_mds_chain(const u64 *in, u64 *out, int chain) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = in[t * 12 + i];
+#pragma unroll 1
+    for (int k = 0; k < chain; k++) {
+#pragma unroll 1
+        for (int r = 0; r < 30; r++) pgl_mds<true>(s, c_pgl.rc[r + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) out[t * 12 + i] = gl_canon(s[i]);
+}
+
 __global__ void __launch_bounds__(BLOCK, MINB) bb_chain(const u32 *in, u32 *out, int chain) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     u32 s[16];
@@ -80,6 +108,26 @@ int main(int argc, char **argv) {
     cudaError_t err = cudaGetLastError();
     printf("GL  block %d occ %d blocks/SM KAT %s: %.3f ms for %zu perms -> %.1f M perm/s (%s)\n", BLOCK, occ, ok ? "ok" : "FAIL",
            best, threads * chain, threads * (double)chain / best * 1e-3, cudaGetErrorString(err));
+    {
+        const double warp_slots = (double)sms * 4 * 1.9625e9;  // SMSP cycles per second at the usual boost clock
+        for (int which = 0; which < 2; which++) {
+            float b2 = 1e30f;
+            for (int rep = 0; rep < 3; rep++) {
+                cudaEventRecord(e0);
+                if (which == 0) gl_sbox_chain<<<threads / BLOCK, BLOCK>>>(d_in, d_out, chain);
+                else gl_mds_chain<<<threads / BLOCK, BLOCK>>>(d_in, d_out, chain);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (ms < b2) b2 = ms;
+            }
+            double calls = (double)threads / 32 * chain * 30 * (which == 0 ? 12 : 1);
+            printf("GL  %s: %.3f ms -> %.1f SMSP cycles per warp-%s\n", which == 0 ? "sbox chain" : "mds chain", b2,
+                   b2 * 1e-3 * warp_slots / calls, which == 0 ? "sbox" : "mds");
+        }
+        printf("GL  permutation: %.0f SMSP cycles per warp-permutation\n", best * 1e-3 * warp_slots / ((double)threads / 32 * chain));
+    }
     // BabyBear
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bb_chain, BLOCK, 0);
     size_t bthreads = (size_t)sms * occ * BLOCK * 8;

@@ -1,21 +1,26 @@
 #!/usr/bin/env python3
-"""Issue-cost estimate of a kernel from its SASS using the costs measured on B200 by tools/microbench/imad_probe.cu:
-IMAD.WIDE / IMAD.HI ~3.6 issue cycles, 32-bit IMAD ~2, everything else ~1 (no overlap between them).
+"""Issue-time estimate of a kernel from its SASS.  Costs fitted on B200 to five measured integer kernels
+(tools/microbench/poseidon_bench.cu: Poseidon-GL old and new forms, its S-box and MDS chains alone, Poseidon2-BB;
+all within 2%): the integer path sustains ~0.70 warp-instructions per cycle per scheduler (1.42 cycles each) whatever
+the opcode (IADD3, IADD3.X, LEA, SEL, LOP3, IMAD.MOV/IADD/X/SHL, 32-bit IMAD), and IMAD.WIDE / IMAD.HI cost 2.6 in
+mixed code (a back-to-back stream of them is pipe-limited at 4.1, tools/microbench/imad_probe.cu).
 usage: sass_cost.py <object-or-cubin> <mangled kernel substring>  -> per-loop and static totals"""
 import re
 import subprocess
 import sys
 
+WIDE = 2.59
+OTHER = 1.42
+FREE = ("NOP",)
+
 
 def cost(op):
     base = op.split(".")
-    if base[0] == "IMAD":
-        if len(base) > 1 and base[1] in ("WIDE", "HI"):
-            return 3.6
-        if len(base) > 1 and base[1] in ("MOV", "IADD", "X", "SHL"):
-            return 1.0
-        return 2.0
-    return 1.0
+    if base[0] == "IMAD" and len(base) > 1 and base[1] in ("WIDE", "HI"):
+        return WIDE
+    if base[0] in FREE:
+        return 0.0
+    return OTHER
 
 
 def main():
