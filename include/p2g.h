@@ -168,6 +168,38 @@ int32_t p2g_permute(p2g_ctx *ctx, int32_t hash, int32_t repr, void *states, uint
 int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, uint32_t log_n, uint32_t num_cols,
                       uint32_t rate_bits, uint32_t flags, const void *in, void *out);
 
+/* ---- FRI commit phase: fri_committed_trees, plonky2/src/fri/prover.rs:83-133.
+ * The Fiat-Shamir challenger stays with the caller; the library does the work between two challenges:
+ *
+ *   p2g_fri_begin(coeffs, values)            lde_polynomial_coeffs / lde_polynomial_values, 2^log_n extension
+ *                                            elements each, an element being its `degree` base coefficients in a
+ *                                            row (F::Extension::as_base_slice); shift starts at F::generator() (:100)
+ *   for arity_bits in reduction_arity_bits:
+ *     p2g_fri_commit_layer(arity_bits, cap_height, cap_out, &tree)
+ *                                            reverse_index_bits + chunks(arity) + flatten + MerkleTree::new (:103-110);
+ *                                            cap_out (host, 2^cap_height digests) is what challenger.observe_cap needs;
+ *                                            `tree` is a device-resident p2g_batch (rows = 2^(log_n - arity_bits)
+ *                                            leaves of arity*degree elements) serving p2g_batch_get_rows / _prove /
+ *                                            _download for the query phase (fri/prover.rs:219-255); free it with
+ *                                            p2g_batch_free
+ *     p2g_fri_fold(beta)                     beta = challenger.get_extension_challenge() (`degree` base elements, in
+ *                                            `repr`): coeffs <- reduce_with_powers over chunks of arity (:116-123),
+ *                                            shift <- shift^arity, values <- coeffs.coset_fft(shift) (:124-125)
+ *   p2g_fri_finish(rate_bits, out, &count)   the final polynomial, truncated to len >> rate_bits (:129-131)
+ *
+ * Errors: the reference's panics map to P2G_ERR_INVALID (cap_height above log2 of the layer's leaf count,
+ * merkle_tree.rs:153-157). Extension degrees: 2 for Goldilocks (X^2 = 7), 4 for BabyBear (X^4 = 11). */
+typedef struct p2g_fri p2g_fri;
+int32_t p2g_fri_begin(p2g_ctx *ctx, int32_t field, int32_t hash, int32_t repr, uint32_t degree, uint32_t log_n,
+                      const void *coeffs, const void *values, uint32_t flags, p2g_fri **out);
+int32_t p2g_fri_commit_layer(p2g_ctx *ctx, p2g_fri *fri, uint32_t arity_bits, uint32_t cap_height, void *cap_out,
+                             p2g_batch **tree_out);
+int32_t p2g_fri_fold(p2g_ctx *ctx, p2g_fri *fri, const void *beta);
+int32_t p2g_fri_finish(p2g_ctx *ctx, p2g_fri *fri, uint32_t rate_bits, void *final_coeffs_out, uint64_t *count_out);
+/* current codeword length (log2) and coset shift (canonical) */
+int32_t p2g_fri_shape(p2g_fri *fri, uint32_t *log_n, uint64_t *shift);
+void p2g_fri_free(p2g_ctx *ctx, p2g_fri *fri);
+
 /* ---- multi-GPU plumbing (one process per GPU).
  * p2g_dev_alloc / p2g_ipc_export / p2g_ipc_import: a device buffer that the other ranks map over NVLink (CUDA IPC).
  * p2g_intt_allgather: the column-sharded inverse NTT of `num_cols` columns (device pointer `values_dev`, column-major)

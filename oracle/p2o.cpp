@@ -752,6 +752,61 @@ static int verify_to_cap(const typename F::E *leaf, size_t leaf_len, size_t inde
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
+
+// ------------------------------------------------------------------------------------------------
+// FRI commit phase, plonky2/src/fri/prover.rs:83-133.
+// Extension fields come from p3's BinomialExtensionField (external): F[X]/(X^D - W) with D = 2, W = 7 for Goldilocks
+// (pinned: the golden proof's FRI query rounds only verify with W = 7, tools/gl_fri_check.py) and D = 4, W = 11 for
+// BabyBear (upstream Plonky3 value; parity unpinned like the other BabyBear constants).
+template <class F>
+struct Ext;
+template <>
+struct Ext<GL> {
+    static const unsigned D = 2;
+    static const uint64_t W = 7;
+};
+template <>
+struct Ext<BB> {
+    static const unsigned D = 4;
+    static const uint64_t W = 11;
+};
+template <class F>
+static void ext_mul(const typename F::E *a, const typename F::E *b, typename F::E *out) {
+    typedef typename F::E E;
+    const unsigned D = Ext<F>::D;
+    E r[2 * Ext<F>::D] = {0};
+    for (unsigned i = 0; i < D; i++)
+        for (unsigned j = 0; j < D; j++) r[i + j] = F::add(r[i + j], F::mul(a[i], b[j]));
+    for (unsigned k = 0; k < D; k++) out[k] = k + 1 < D ? F::add(r[k], F::mul((E)Ext<F>::W, r[k + D])) : r[k];
+}
+
+// One loop iteration after the challenge (:114-125): coeffs <- chunks_exact(arity).map(reduce_with_powers(chunk, beta))
+// (plonk_common.rs:124-136: Horner from the last term), shift <- shift^arity, values <- coeffs.coset_fft(shift).
+// The FFT of extension elements uses base-field roots (fft.rs:12-31), so it acts on each coordinate separately.
+template <class F>
+static void fri_fold_layer(const typename F::E *coeffs, unsigned log_n, unsigned arity_bits, const typename F::E *beta,
+                           uint64_t shift_in, typename F::E *coeffs_out, typename F::E *values_out, uint64_t *shift_out) {
+    typedef typename F::E E;
+    const unsigned D = Ext<F>::D;
+    const size_t n_out = (size_t)1 << (log_n - arity_bits), arity = (size_t)1 << arity_bits;
+    for (size_t i = 0; i < n_out; i++) {
+        E sum[Ext<F>::D] = {0}, t[Ext<F>::D];
+        for (size_t j = arity; j-- > 0;) {
+            ext_mul<F>(sum, beta, t);
+            for (unsigned k = 0; k < D; k++) sum[k] = F::add(t[k], coeffs[(i * arity + j) * D + k]);
+        }
+        for (unsigned k = 0; k < D; k++) coeffs_out[i * D + k] = sum[k];
+    }
+    E shift = f_pow<F>((E)shift_in, arity);
+    *shift_out = shift;
+    std::vector<E> col(n_out);
+    for (unsigned k = 0; k < D; k++) {
+        for (size_t i = 0; i < n_out; i++) col[i] = coeffs_out[i * D + k];
+        coset_fft<F>(col.data(), log_n - arity_bits, shift, 0);
+        for (size_t i = 0; i < n_out; i++) values_out[i * D + k] = col[i];
+    }
+}
+
 extern "C" {
 
 int p2o_max_threads(void) {
@@ -867,4 +922,33 @@ int p2o_verify_merkle_proof_to_cap(int field, const void *leaf, size_t leaf_len,
 
 int p2o_commit(p2o_commit_desc *d) { return d->field == P2O_FIELD_GL ? commit<GL>(d) : commit<BB>(d); }
 
+unsigned p2o_ext_degree(int field) { return field == P2O_FIELD_GL ? Ext<GL>::D : Ext<BB>::D; }
+uint64_t p2o_ext_w(int field) { return field == P2O_FIELD_GL ? Ext<GL>::W : Ext<BB>::W; }
+void p2o_ext_mul(int field, const void *a, const void *b, void *out) {
+    if (field == P2O_FIELD_GL)
+        ext_mul<GL>((const uint64_t *)a, (const uint64_t *)b, (uint64_t *)out);
+    else
+        ext_mul<BB>((const uint32_t *)a, (const uint32_t *)b, (uint32_t *)out);
+}
+void p2o_fri_fold_layer(int field, const void *coeffs, unsigned log_n, unsigned arity_bits, const void *beta,
+                        uint64_t shift_in, void *coeffs_out, void *values_out, uint64_t *shift_out) {
+    if (field == P2O_FIELD_GL)
+        fri_fold_layer<GL>((const uint64_t *)coeffs, log_n, arity_bits, (const uint64_t *)beta, shift_in,
+                           (uint64_t *)coeffs_out, (uint64_t *)values_out, shift_out);
+    else
+        fri_fold_layer<BB>((const uint32_t *)coeffs, log_n, arity_bits, (const uint32_t *)beta, shift_in,
+                           (uint32_t *)coeffs_out, (uint32_t *)values_out, shift_out);
+}
+// reverse_index_bits_in_place(values) + chunks(arity) + flatten (:103-109): an extension element is 16 bytes in both
+// configurations, and flattening consecutive elements is the identity on memory, so the leaf matrix
+// [n >> arity_bits][arity * D] is the bit-reversed copy of the values.
+void p2o_fri_layer_leaves(int field, const void *values, unsigned log_n, void *leaves_out) {
+    (void)field;
+    struct E16 {
+        uint64_t a, b;
+    };
+    size_t n = (size_t)1 << log_n;
+    memcpy(leaves_out, values, n * sizeof(E16));
+    reverse_index_bits_in_place((E16 *)leaves_out, log_n);
+}
 }  // extern "C"

@@ -111,6 +111,17 @@ typedef struct {
 /* PolynomialBatch::from_values / from_coeffs. returns 0 on success, -1 on a condition the reference panics on. */
 int p2o_commit(p2o_commit_desc *desc);
 
+/* FRI commit phase (plonky2/src/fri/prover.rs:83-133).  An extension element is D base elements in a row. */
+unsigned p2o_ext_degree(int field);  /* 2 (GL), 4 (BB) */
+uint64_t p2o_ext_w(int field);       /* X^D = W: 7 (GL, pinned by the golden FRI proof), 11 (BB, unpinned) */
+void p2o_ext_mul(int field, const void *a, const void *b, void *out);
+/* leaves of one layer tree: [n >> arity_bits][arity * D] = the bit-reversed values (:103-109) */
+void p2o_fri_layer_leaves(int field, const void *values, unsigned log_n, void *leaves_out);
+/* after the challenge beta (:114-125): folded coefficients [n >> arity_bits][D], shift^arity, and the folded
+ * polynomial's evaluations on the new coset, natural order */
+void p2o_fri_fold_layer(int field, const void *coeffs, unsigned log_n, unsigned arity_bits, const void *beta,
+                        uint64_t shift_in, void *coeffs_out, void *values_out, uint64_t *shift_out);
+
 int p2o_max_threads(void);
 
 #ifdef __cplusplus

@@ -72,6 +72,13 @@ def load(native: bool = False) -> ctypes.CDLL:
     lib.p2o_commit.argtypes = [ctypes.POINTER(CommitDesc)]
     lib.p2o_commit.restype = ci
     lib.p2o_max_threads.restype = ci
+    lib.p2o_ext_degree.argtypes = [ci]
+    lib.p2o_ext_degree.restype = ui
+    lib.p2o_ext_w.argtypes = [ci]
+    lib.p2o_ext_w.restype = u64
+    lib.p2o_ext_mul.argtypes = [ci, vp, vp, vp]
+    lib.p2o_fri_layer_leaves.argtypes = [ci, vp, ui, vp]
+    lib.p2o_fri_fold_layer.argtypes = [ci, vp, ui, ui, vp, u64, vp, vp, ctypes.POINTER(u64)]
     _LIBS[native] = lib
     return lib
 
@@ -198,3 +205,58 @@ def commit(field, columns, input_kind, rate_bits, cap_height, salts=None, thread
 
 def max_threads() -> int:
     return load().p2o_max_threads()
+
+
+# ---- FRI commit phase (plonky2/src/fri/prover.rs:83-133) -------------------------------------------------------------
+def ext_degree(field) -> int:
+    return int(load().p2o_ext_degree(field))
+
+
+def ext_mul(field, a, b) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=DTYPE[field])
+    b = np.ascontiguousarray(b, dtype=DTYPE[field])
+    out = np.empty_like(a)
+    load().p2o_ext_mul(field, a.ctypes.data, b.ctypes.data, out.ctypes.data)
+    return out
+
+
+def fri_layer_leaves(field, values, arity_bits) -> np.ndarray:
+    """values [n][D] -> leaf matrix [n >> arity_bits][D << arity_bits] (:103-109)"""
+    values = np.ascontiguousarray(values, dtype=DTYPE[field])
+    n, d = values.shape
+    out = np.empty_like(values)
+    load().p2o_fri_layer_leaves(field, values.ctypes.data, n.bit_length() - 1, out.ctypes.data)
+    return out.reshape(n >> arity_bits, d << arity_bits)
+
+
+def fri_fold_layer(field, coeffs, arity_bits, beta, shift):
+    """(:114-125) -> (folded coeffs [n >> a][D], their coset evaluations [n >> a][D] in natural order, shift^arity)"""
+    coeffs = np.ascontiguousarray(coeffs, dtype=DTYPE[field])
+    beta = np.ascontiguousarray(beta, dtype=DTYPE[field])
+    n, d = coeffs.shape
+    co = np.empty((n >> arity_bits, d), dtype=DTYPE[field])
+    vo = np.empty((n >> arity_bits, d), dtype=DTYPE[field])
+    so = ctypes.c_uint64()
+    load().p2o_fri_fold_layer(field, coeffs.ctypes.data, n.bit_length() - 1, arity_bits, beta.ctypes.data, int(shift),
+                              co.ctypes.data, vo.ctypes.data, ctypes.byref(so))
+    return co, vo, int(so.value)
+
+
+def fri_committed_trees(field, coeffs, values, challenger, reduction_arity_bits, rate_bits, cap_height):
+    """fri_committed_trees (:83-133) composed from the pieces above; `challenger` is any object with observe_cap /
+    get_extension_challenge / observe_extension_elements (tests pass the package's Challenger with this module's
+    permutation injected).  Returns ([(leaves, digests, cap)], final_coeffs)."""
+    trees = []
+    shift = int(load().p2o_generator(field))
+    coeffs = np.ascontiguousarray(coeffs, dtype=DTYPE[field])
+    values = np.ascontiguousarray(values, dtype=DTYPE[field])
+    for arity_bits in reduction_arity_bits:
+        leaves = fri_layer_leaves(field, values, arity_bits)
+        digests, cap = merkle_tree(field, leaves, cap_height)
+        trees.append((leaves, digests, cap))
+        challenger.observe_cap(cap)
+        beta = challenger.get_extension_challenge()
+        coeffs, values, shift = fri_fold_layer(field, coeffs, arity_bits, beta, shift)
+    final = coeffs[: coeffs.shape[0] >> rate_bits].copy()
+    challenger.observe_extension_elements(final)
+    return trees, final

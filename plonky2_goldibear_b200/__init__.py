@@ -7,8 +7,11 @@ from .fields import GOLDILOCKS, BABYBEAR, Field
 from ._lib import Context, P2GError, library_path, load_library
 from .merkle_tree import MerkleTree, MerkleCap
 from .fri_oracle import PolynomialBatch, ProvingProcessInfo, SALT_SIZE
+from .challenger import Challenger
+from .fri_prover import FriConfig, FriParams, fri_committed_trees
 
 __all__ = [
     "GOLDILOCKS", "BABYBEAR", "Field", "Context", "P2GError", "library_path", "load_library",
     "MerkleTree", "MerkleCap", "PolynomialBatch", "ProvingProcessInfo", "SALT_SIZE",
+    "Challenger", "FriConfig", "FriParams", "fri_committed_trees",
 ]

@@ -51,6 +51,7 @@ EXPORTS = [
     "p2g_release_workspace", "p2g_stream", "p2g_kernel_launches", "p2g_batch_get_rows", "p2g_batch_prove",
     "p2g_batch_download", "p2g_batch_shape", "p2g_batch_free", "p2g_dev_alloc", "p2g_dev_free", "p2g_ipc_export",
     "p2g_ipc_import", "p2g_ipc_close", "p2g_intt_allgather", "p2g_memcpy_async",
+    "p2g_fri_begin", "p2g_fri_commit_layer", "p2g_fri_fold", "p2g_fri_finish", "p2g_fri_shape", "p2g_fri_free",
 ]
 
 
@@ -124,6 +125,18 @@ def load_library() -> ctypes.CDLL:
         lib.p2g_intt_allgather.restype = i32
         lib.p2g_memcpy_async.argtypes = [vp, vp, vp, ctypes.c_size_t, i32]
         lib.p2g_memcpy_async.restype = i32
+        lib.p2g_fri_begin.argtypes = [vp, i32, i32, i32, u32, u32, vp, vp, u32, ctypes.POINTER(vp)]
+        lib.p2g_fri_begin.restype = i32
+        lib.p2g_fri_commit_layer.argtypes = [vp, vp, u32, u32, vp, ctypes.POINTER(vp)]
+        lib.p2g_fri_commit_layer.restype = i32
+        lib.p2g_fri_fold.argtypes = [vp, vp, vp]
+        lib.p2g_fri_fold.restype = i32
+        lib.p2g_fri_finish.argtypes = [vp, vp, u32, vp, ctypes.POINTER(u64)]
+        lib.p2g_fri_finish.restype = i32
+        lib.p2g_fri_shape.argtypes = [vp, ctypes.POINTER(u32), ctypes.POINTER(u64)]
+        lib.p2g_fri_shape.restype = i32
+        lib.p2g_fri_free.argtypes = [vp, vp]
+        lib.p2g_fri_free.restype = None
         _LIB = lib
         return lib
 

@@ -78,6 +78,20 @@ struct p2g_batch {
     void *leaves = nullptr, *digests = nullptr, *cap = nullptr, *coeffs = nullptr;
 };
 
+// State of one FRI commit phase between layers (fri/prover.rs:83-133): the coefficient vector of the current
+// codeword, one extension coordinate per column, and its evaluations in bit-reversed order.
+struct p2g_fri {
+    int field = 0, hash = 0, repr = 0;
+    unsigned degree = 0;    // D, base elements per extension element
+    size_t elem = 0;
+    unsigned log_n = 0;     // current codeword length
+    uint64_t shift = 0;     // coset shift of the current evaluations (canonical)
+    void *coeffs = nullptr; // [D][n]
+    void *values = nullptr; // [n][D], bit-reversed order; null once a layer tree owns it
+    size_t coeffs_bytes = 0, values_bytes = 0;
+    int pending_arity_bits = -1;  // set by commit_layer, consumed by fold
+};
+
 struct p2g_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -950,6 +964,229 @@ int32_t p2g_merkle_finish_cap(p2g_ctx *ctx, int32_t field, int32_t hash, int32_t
     m.digests_out = top_digests_out;
     m.cap_out = cap_out;
     return merkle_locked(ctx, &m);
+}
+
+// ---- FRI commit phase ---------------------------------------------------------------------------------
+static uint64_t ext_w(const FieldInfo &f) { return f.id == FIELD_GL ? 7 : 11; }  // X^D = W of the binomial extension
+static unsigned ext_degree(const FieldInfo &f) { return f.id == FIELD_GL ? 2 : 4; }
+
+int32_t p2g_fri_begin(p2g_ctx *ctx, int32_t field, int32_t hash, int32_t repr_in, uint32_t degree, uint32_t log_n,
+                      const void *coeffs, const void *values, uint32_t flags, p2g_fri **out) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!out) return ctx->fail(P2G_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    const FieldInfo *fp;
+    int rc = check_field_hash(ctx, field, hash, &fp);
+    if (rc) return rc;
+    const FieldInfo &f = *fp;
+    const int repr = f.id == FIELD_BB ? repr_in : 0;
+    if (repr != P2G_REPR_CANONICAL && repr != P2G_REPR_MONTY_R32) return ctx->fail(P2G_ERR_INVALID, "bad repr %d", repr);
+    if (degree != ext_degree(f))
+        return ctx->fail(P2G_ERR_UNSUPPORTED, "extension degree %u: the GPU path has D = 2 for Goldilocks and D = 4 for BabyBear", degree);
+    if (log_n > f.two_adicity || log_n > 30) return ctx->fail(P2G_ERR_INVALID, "codeword length 2^%u exceeds the field's two-adicity", log_n);
+    if (!coeffs || !values) return ctx->fail(P2G_ERR_INVALID, "coeffs / values is NULL");
+    const uint64_t n = (uint64_t)1 << log_n;
+    const size_t bytes = (size_t)n * degree * f.elem;
+    const bool dev_in = flags & P2G_FLAG_DEVICE_INPUT;
+    p2g_fri *s = new p2g_fri();
+    s->field = field;
+    s->hash = hash;
+    s->repr = repr;
+    s->degree = degree;
+    s->elem = f.elem;
+    s->log_n = log_n;
+    s->shift = f.generator;  // prover.rs:100
+    s->coeffs_bytes = s->values_bytes = std::max<size_t>(bytes, 32);
+    s->coeffs = pool_alloc(ctx, s->coeffs_bytes);
+    s->values = pool_alloc(ctx, s->values_bytes);
+    struct Guard {
+        p2g_ctx *ctx;
+        p2g_fri *s;
+        ~Guard() {
+            if (!s) return;
+            cudaStreamSynchronize(ctx->stream);
+            pool_free(ctx, s->coeffs, s->coeffs_bytes);
+            pool_free(ctx, s->values, s->values_bytes);
+            delete s;
+        }
+    } guard{ctx, s};
+    if (!s->coeffs || !s->values) return ctx->fail(P2G_ERR_OOM, "device allocation for the FRI state failed");
+    cudaStream_t st = ctx->stream;
+    const void *src = coeffs;
+    if (!dev_in) {
+        if ((rc = ensure(ctx, ctx->in, bytes))) return rc;
+        CK(cudaMemcpyAsync(ctx->in.ptr, coeffs, bytes, cudaMemcpyHostToDevice, st));
+        src = ctx->in.ptr;
+    }
+    launch_fri_split(f.id, src, n, s->coeffs, st, &ctx->launches);
+    src = values;
+    if (!dev_in) {
+        CK(cudaMemcpyAsync(ctx->in.ptr, values, bytes, cudaMemcpyHostToDevice, st));
+        src = ctx->in.ptr;
+    }
+    launch_fri_bitrev16(src, log_n, s->values, st, &ctx->launches);  // reverse_index_bits_in_place, prover.rs:103
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    guard.s = nullptr;
+    *out = s;
+    return P2G_OK;
+}
+
+int32_t p2g_fri_commit_layer(p2g_ctx *ctx, p2g_fri *s, uint32_t arity_bits, uint32_t cap_height, void *cap_out,
+                             p2g_batch **tree_out) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!s || !tree_out) return ctx->fail(P2G_ERR_INVALID, "state / tree_out is NULL");
+    if (!s->values || s->pending_arity_bits >= 0) return ctx->fail(P2G_ERR_INVALID, "layer already committed: call p2g_fri_fold first");
+    if (arity_bits > s->log_n) return ctx->fail(P2G_ERR_INVALID, "arity 2^%u exceeds the codeword length 2^%u", arity_bits, s->log_n);
+    const FieldInfo *fp;
+    int rc = check_field_hash(ctx, s->field, s->hash, &fp);
+    if (rc) return rc;
+    const FieldInfo &f = *fp;
+    const unsigned tree_log = s->log_n - arity_bits;
+    if (cap_height > tree_log)
+        return ctx->fail(P2G_ERR_INVALID, "cap_height=%u should be at most log2(leaves.len())=%u", cap_height, tree_log);
+    p2g_batch *b = new p2g_batch();
+    b->field = f.id;
+    b->elem = f.elem;
+    b->rows = (uint64_t)1 << tree_log;
+    b->width = (uint64_t)s->degree << arity_bits;  // flatten(chunk): arity extension elements, prover.rs:104-108
+    b->num_cols = 0;
+    b->n = 0;
+    b->log_leaves = tree_log;
+    b->cap_height = cap_height;
+    b->num_cap = (uint64_t)1 << cap_height;
+    b->num_digests = 2 * (b->rows - b->num_cap);
+    b->digests_bytes = std::max<size_t>(32, b->num_digests * 32);
+    b->cap_bytes = b->num_cap * 32;
+    b->digests = pool_alloc(ctx, b->digests_bytes);
+    b->cap = pool_alloc(ctx, b->cap_bytes);
+    if (!b->digests || !b->cap) {
+        pool_free(ctx, b->digests, b->digests_bytes);
+        pool_free(ctx, b->cap, b->cap_bytes);
+        delete b;
+        return ctx->fail(P2G_ERR_OOM, "device allocation for the layer tree failed");
+    }
+    // the bit-reversed evaluations ARE the leaf matrix; the tree takes them over
+    b->leaves = s->values;
+    b->leaves_bytes = s->values_bytes;
+    s->values = nullptr;
+    s->values_bytes = 0;
+    cudaStream_t st = ctx->stream;
+    TreeShape tree = {tree_log, cap_height, b->digests, b->cap};
+    launch_leaf_hash(f.id, s->repr, b->leaves, b->width, (uint32_t)b->width, 0, b->rows, tree, st, &ctx->launches);
+    launch_tree_levels(f.id, s->repr, tree, st, &ctx->launches);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && cap_out) e = cudaMemcpyAsync(cap_out, b->cap, b->cap_bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    s->pending_arity_bits = (int)arity_bits;
+    *tree_out = b;  // handed over even on a CUDA error so the caller can free it
+    if (e != cudaSuccess) return ctx->fail(P2G_ERR_CUDA, "layer tree failed: %s", cudaGetErrorString(e));
+    return P2G_OK;
+}
+
+int32_t p2g_fri_fold(p2g_ctx *ctx, p2g_fri *s, const void *beta) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!s || !beta) return ctx->fail(P2G_ERR_INVALID, "state / beta is NULL");
+    if (s->pending_arity_bits < 0) return ctx->fail(P2G_ERR_INVALID, "no committed layer to fold: call p2g_fri_commit_layer first");
+    const FieldInfo *fp;
+    int rc = check_field_hash(ctx, s->field, s->hash, &fp);
+    if (rc) return rc;
+    const FieldInfo &f = *fp;
+    const unsigned a = (unsigned)s->pending_arity_bits, D = s->degree;
+    const unsigned log_out = s->log_n - a;
+    const uint64_t n_in = (uint64_t)1 << s->log_n, n_out = (uint64_t)1 << log_out;
+    // beta arrives in the caller's representation; the kernel wants the internal one
+    uint64_t beta_int[4] = {0, 0, 0, 0};
+    for (unsigned k = 0; k < D; k++) {
+        uint64_t v = f.id == FIELD_GL ? ((const uint64_t *)beta)[k] : ((const uint32_t *)beta)[k];
+        if (f.id == FIELD_GL)
+            beta_int[k] = v >= P2G_GL_P ? v - P2G_GL_P : v;
+        else if (s->repr == P2G_REPR_MONTY_R32)
+            beta_int[k] = v % P2G_BB_P;
+        else
+            beta_int[k] = f_internal(f, v % P2G_BB_P);
+    }
+    const size_t out_bytes = std::max<size_t>((size_t)n_out * D * f.elem, 32);
+    void *nc = pool_alloc(ctx, out_bytes), *nv = pool_alloc(ctx, out_bytes);
+    if (!nc || !nv) {
+        pool_free(ctx, nc, out_bytes);
+        pool_free(ctx, nv, out_bytes);
+        return ctx->fail(P2G_ERR_OOM, "device allocation for the folded layer failed");
+    }
+    cudaStream_t st = ctx->stream;
+    launch_fri_fold(f.id, s->repr, s->coeffs, n_in, a, beta_int, f_internal(f, ext_w(f)), nc, st, &ctx->launches);
+    const uint64_t shift = f_pow(f, s->shift, (uint64_t)1 << a);  // prover.rs:124
+    rc = 0;
+    if (log_out == 0) {
+        // a single coefficient is its own evaluation
+        for (unsigned k = 0; k < D && !rc; k++)
+            if (cudaMemcpyAsync((char *)nv + k * f.elem, (char *)nc + k * f.elem, f.elem, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+                rc = ctx->fail(P2G_ERR_CUDA, "copy failed");
+    } else {
+        if (log_out > MAX_TILE_LOG) rc = ensure(ctx, ctx->tmp, (size_t)n_out * D * f.elem);
+        // coset_fft(shift): D base-field transforms, written as rows of D in bit-reversed order = the next leaf matrix
+        if (!rc) rc = run_transform(ctx, f, s->repr, false, log_out, D, nc, ctx->tmp.ptr, nv, D, shift, 0);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) rc = ctx->fail(P2G_ERR_CUDA, "fold failed: %s", cudaGetErrorString(e));
+    if (rc) {
+        pool_free(ctx, nc, out_bytes);
+        pool_free(ctx, nv, out_bytes);
+        return rc;
+    }
+    pool_free(ctx, s->coeffs, s->coeffs_bytes);
+    s->coeffs = nc;
+    s->values = nv;
+    s->coeffs_bytes = s->values_bytes = out_bytes;
+    s->log_n = log_out;
+    s->shift = shift;
+    s->pending_arity_bits = -1;
+    return P2G_OK;
+}
+
+int32_t p2g_fri_finish(p2g_ctx *ctx, p2g_fri *s, uint32_t rate_bits, void *final_coeffs_out, uint64_t *count_out) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!s) return ctx->fail(P2G_ERR_INVALID, "state is NULL");
+    if (s->pending_arity_bits >= 0) return ctx->fail(P2G_ERR_INVALID, "a committed layer has not been folded");
+    const uint64_t n = (uint64_t)1 << s->log_n;
+    const uint64_t count = rate_bits >= 64 ? 0 : n >> rate_bits;  // coeffs.truncate(len >> rate_bits), prover.rs:129-131
+    if (count_out) *count_out = count;
+    if (final_coeffs_out && count) {
+        std::vector<unsigned char> cols((size_t)count * s->degree * s->elem);
+        for (unsigned k = 0; k < s->degree; k++)
+            CK(cudaMemcpyAsync(cols.data() + (size_t)k * count * s->elem, (char *)s->coeffs + (size_t)k * n * s->elem, count * s->elem,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (uint64_t i = 0; i < count; i++)
+            for (unsigned k = 0; k < s->degree; k++)
+                memcpy((char *)final_coeffs_out + ((size_t)i * s->degree + k) * s->elem, cols.data() + ((size_t)k * count + i) * s->elem, s->elem);
+    }
+    return P2G_OK;
+}
+
+int32_t p2g_fri_shape(p2g_fri *s, uint32_t *log_n, uint64_t *shift) {
+    if (!s) return P2G_ERR_INVALID;
+    if (log_n) *log_n = s->log_n;
+    if (shift) *shift = s->shift;
+    return P2G_OK;
+}
+
+void p2g_fri_free(p2g_ctx *ctx, p2g_fri *s) {
+    if (!ctx || !s) return;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    pool_free(ctx, s->coeffs, s->coeffs_bytes);
+    pool_free(ctx, s->values, s->values_bytes);
+    delete s;
 }
 
 int32_t p2g_permute(p2g_ctx *ctx, int32_t hash, int32_t repr, void *states, uint64_t count) {

@@ -83,4 +83,14 @@ void launch_salt_scatter(int field, const void *salts, uint32_t num_salt, uint32
 void launch_leaves_to_columns(int field, const void *leaves, uint64_t pitch, uint32_t num_cols, uint32_t log_N,
                               void *out, cudaStream_t stream, uint64_t *launches);
 
+// ---- fri.cu ------------------------------------------------------------------------------------
+// out[i] = in[bitrev(i)], 16-byte elements (one extension element: 2 x u64 or 4 x u32)
+void launch_fri_bitrev16(const void *in, uint32_t log_n, void *out, cudaStream_t stream, uint64_t *launches);
+// cols[k][i] = rows[i][k] for the D coordinates of n extension elements
+void launch_fri_split(int field, const void *rows, uint64_t n, void *cols, cudaStream_t stream, uint64_t *launches);
+// coeffs_out[k][i] = coordinate k of sum_j coeffs_in[.][i*arity + j] * beta^j; beta and w (X^D = w) in internal form
+void launch_fri_fold(int field, int repr, const void *coeffs_in, uint64_t n_in, uint32_t arity_bits,
+                     const uint64_t *beta_internal, uint64_t w_internal, void *coeffs_out, cudaStream_t stream,
+                     uint64_t *launches);
+
 }  // namespace p2g

@@ -101,6 +101,42 @@ def reduce_with(alpha, values):
     return acc, len(values)
 
 
+def fri_fold_chain(x_index, old_eval, step_evals, arity_bits, fri_betas, final_poly, lde_bits, generator, two_adic_generator):
+    """The folding half of fri_verifier_query_round (verifier.rs:209-255): starting from the value `old_eval` the first
+    layer must hold at leaf position x_index, check every layer's opened coset against the previous fold
+    (compute_evaluation, verifier.rs:19-46) and the last fold against the final polynomial."""
+    subgroup_x = generator * pow(two_adic_generator(lde_bits), reverse_bits(x_index, lde_bits), P) % P
+    for i, ab in enumerate(arity_bits):
+        arity = 1 << ab
+        evals = step_evals[i]
+        coset_index, within = x_index >> ab, x_index & (arity - 1)
+        assert evals[within] == old_eval, "FRI layer %d: committed value differs from the folded one" % i
+        # compute_evaluation (verifier.rs:19-46)
+        g = two_adic_generator(ab)
+        ordered = [evals[reverse_bits(j, ab)] for j in range(arity)]
+        start = subgroup_x * pow(g, arity - reverse_bits(within, ab), P) % P
+        xs = [base(start * pow(g, j, P) % P) for j in range(arity)]
+        beta = fri_betas[i]
+        lx = (1, 0)
+        for xj in xs:
+            lx = e_mul(lx, e_sub(beta, xj))
+        acc = (0, 0)
+        for a in range(arity):
+            wa = (1, 0)
+            for b in range(arity):
+                if a != b:
+                    wa = e_mul(wa, e_sub(xs[a], xs[b]))
+            term = e_mul(e_inv(e_mul(wa, e_sub(beta, xs[a]))), ordered[a])
+            acc = e_add(acc, term)
+        old_eval = e_mul(lx, acc)
+        subgroup_x = pow(subgroup_x, arity, P)
+        x_index = coset_index
+    fin = (0, 0)
+    for cf in reversed(final_poly):
+        fin = e_add(e_mul(fin, base(subgroup_x)), cf)
+    assert fin == old_eval, "final polynomial evaluation is invalid"
+
+
 def verify(fx, permute, generator, two_adic_generator):
     """fx: the fixture dict (tests/golden/gl_proof_fri.json).  Raises AssertionError on any failed check; returns a summary."""
     H = lambda xs: [int(x, 16) for x in xs]
@@ -169,35 +205,7 @@ def verify(fx, permute, generator, two_adic_generator):
             denominator = e_sub(base(subgroup_x), point)
             total = e_mul(total, e_pow(fri_alpha, cnt))  # alpha.shift(sum): the count of the reduce just done
             total = e_add(total, e_mul(numerator, e_inv(denominator)))
-        old_eval = total
-        for i, ab in enumerate(arity_bits):
-            arity = 1 << ab
-            evals = [tuple(H(e)) for e in q["steps"][i]]
-            coset_index, within = x_index >> ab, x_index & (arity - 1)
-            assert evals[within] == old_eval, "FRI layer %d: committed value differs from the folded one" % i
-            # compute_evaluation (verifier.rs:19-46)
-            g = two_adic_generator(ab)
-            ordered = [evals[reverse_bits(j, ab)] for j in range(arity)]
-            start = subgroup_x * pow(g, arity - reverse_bits(within, ab), P) % P
-            xs = [base(start * pow(g, j, P) % P) for j in range(arity)]
-            beta = fri_betas[i]
-            lx = (1, 0)
-            for xj in xs:
-                lx = e_mul(lx, e_sub(beta, xj))
-            acc = (0, 0)
-            for a in range(arity):
-                wa = (1, 0)
-                for b in range(arity):
-                    if a != b:
-                        wa = e_mul(wa, e_sub(xs[a], xs[b]))
-                term = e_mul(e_inv(e_mul(wa, e_sub(beta, xs[a]))), ordered[a])
-                acc = e_add(acc, term)
-            old_eval = e_mul(lx, acc)
-            subgroup_x = pow(subgroup_x, arity, P)
-            x_index = coset_index
-        fin = (0, 0)
-        for cf in reversed(final_poly):
-            fin = e_add(e_mul(fin, base(subgroup_x)), cf)
-        assert fin == old_eval, "final polynomial evaluation is invalid"
+        fri_fold_chain(x_index, total, [[tuple(H(e)) for e in step] for step in q["steps"]], arity_bits, fri_betas, final_poly,
+                       lde_bits, generator, two_adic_generator)
         checked += 1
     return {"queries_checked": checked, "query_indices": indices, "zeta": zeta}
