@@ -479,6 +479,11 @@ def run_ours(args, field_name):
     }
     if G == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, field_name)
+    if G == 1 and not args.no_fri:
+        try:
+            line["fri_commit_phase"] = fri_commit_phase_bench(args, field_name, ctx, p2g)
+        except Exception as e:  # a secondary measurement must not cost the headline line
+            line["fri_commit_phase"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if G > 1:
@@ -513,6 +518,51 @@ def cpu_baseline(args, field_name):
             "stage_ms": {k: v * 1e3 for k, v in zip(("IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree"), stages)}}
 
 
+def fri_commit_phase_bench(args, field_name, ctx, p2g):
+    """fri_committed_trees (fri/prover.rs:83-133) on the codeword of this workload's LDE size, arity 16
+    down to a 2^rate_bits..2^(rate_bits+4)-coefficient final polynomial (ConstantArityBits(4, 5)), host arrays in, caps and
+    final polynomial out, layer trees left on the device for the query phase.  Timed end to end on the host clock (the
+    challenger sits between the device calls); the CPU figure is the oracle's restatement of the same function."""
+    from oracle import p2o
+    fid = p2o.GL if field_name == "gl" else p2o.BB
+    f = p2g.GOLDILOCKS if field_name == "gl" else p2g.BABYBEAR
+    d = f.extension_degree
+    degree_bits, r, h = args.log_n, args.rate_bits, args.cap_height
+    arities = []
+    while degree_bits - sum(arities) > 5 and degree_bits + r - sum(arities) - 4 >= h:
+        arities.append(4)
+    n = 1 << (degree_bits + r)
+    rng = np.random.default_rng(7)
+    coeffs = ctx.pinned_empty((n, d), f.dtype)
+    values = ctx.pinned_empty((n, d), f.dtype)
+    coeffs[:] = 0
+    coeffs[: 1 << degree_bits] = rng.integers(0, f.order, size=(1 << degree_bits, d), dtype=np.uint64).astype(f.dtype)
+    values[:] = rng.integers(0, f.order, size=(n, d), dtype=np.uint64).astype(f.dtype)  # any codeword times the same
+    params = p2g.FriParams(p2g.FriConfig(r, h), arities)
+    best = None
+    for it in range(3):
+        ch = p2g.Challenger(f, ctx=ctx)
+        t0 = time.perf_counter()
+        trees, final = p2g.fri_committed_trees(f, coeffs, values, ch, params, ctx=ctx)
+        dt = time.perf_counter() - t0
+        for t in trees:
+            t.free()
+        best = dt if best is None or dt < best else best
+    out = {"ms": best * 1e3, "log_n": degree_bits + r, "extension_degree": d, "reduction_arity_bits": arities, "cap_height": h,
+           "timing": "host wall clock around fri_committed_trees, pinned host arrays in (%.0f MB H2D), best of 3" % (2 * coeffs.nbytes / 1e6)}
+    if not args.no_cpu_baseline:
+        cpu_best = None
+        for it in range(2):
+            ch = p2g.Challenger(f, permute=lambda s: p2o.permute(fid, s))
+            t0 = time.perf_counter()
+            p2o.fri_committed_trees(fid, coeffs, values, ch, arities, r, h)
+            dt = time.perf_counter() - t0
+            cpu_best = dt if cpu_best is None or dt < cpu_best else cpu_best
+        out["cpu_port_ms"] = cpu_best * 1e3
+        out["cpu_port"] = "oracle restatement (fold single-threaded, Merkle trees on all host threads), best of 2"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -530,6 +580,7 @@ def main():
                     help="multi-GPU coefficient exchange: inverse NTT with the all-gather fused into its epilogue over "
                          "peer memory (default), or a separate ncclAllGather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fri", action="store_true", help="skip the secondary FRI commit-phase measurement")
     ap.add_argument("--cpu-sample-log-n", type=int, default=16)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

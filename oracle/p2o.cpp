@@ -807,6 +807,39 @@ static void fri_fold_layer(const typename F::E *coeffs, unsigned log_n, unsigned
     }
 }
 
+
+// fri_proof_of_work, fri/prover.rs:136-188: the reference searches 0..=p-1 in parallel and takes any hit; the oracle
+// returns the SMALLEST hit (sequential semantics), which is what the GPU path is specified to return too.
+template <class F>
+static int fri_pow(const typename F::E *state, const typename F::E *input, unsigned input_len, unsigned min_leading_zeros,
+                   uint64_t *witness) {
+    typedef typename F::E E;
+    E base[F::WIDTH];
+    for (unsigned i = 0; i < F::WIDTH; i++) base[i] = state[i];
+    for (unsigned i = 0; i < input_len; i++) base[i] = input[i];  // duplex_intermediate_state :166-168
+    const uint64_t last = F::P - 1, chunk = 1 << 14;
+    for (uint64_t start = 0; start <= last; start += chunk) {
+        uint64_t end = std::min<uint64_t>(last, start + chunk - 1);
+        uint64_t best = ~0ull;
+#pragma omp parallel for reduction(min : best)
+        for (uint64_t c = start; c <= end; c++) {
+            E s[F::WIDTH];
+            for (unsigned i = 0; i < F::WIDTH; i++) s[i] = base[i];
+            s[input_len] = (E)c;
+            Perm<F>::permute(s);
+            uint64_t resp = s[RATE - 1];  // squeeze().last() :175
+            unsigned lz = resp ? (unsigned)__builtin_clzll(resp) : 64u;
+            if (lz >= min_leading_zeros && c < best) best = c;
+        }
+        if (best != ~0ull) {
+            *witness = best;
+            return 0;
+        }
+        if (start + chunk < start) break;
+    }
+    return -1;
+}
+
 extern "C" {
 
 int p2o_max_threads(void) {
@@ -950,5 +983,11 @@ void p2o_fri_layer_leaves(int field, const void *values, unsigned log_n, void *l
     size_t n = (size_t)1 << log_n;
     memcpy(leaves_out, values, n * sizeof(E16));
     reverse_index_bits_in_place((E16 *)leaves_out, log_n);
+}
+int p2o_fri_pow(int field, const void *state, const void *input, unsigned input_len, unsigned min_leading_zeros,
+                uint64_t *witness) {
+    if (field == P2O_FIELD_GL)
+        return fri_pow<GL>((const uint64_t *)state, (const uint64_t *)input, input_len, min_leading_zeros, witness);
+    return fri_pow<BB>((const uint32_t *)state, (const uint32_t *)input, input_len, min_leading_zeros, witness);
 }
 }  // extern "C"

@@ -122,6 +122,11 @@ void p2o_fri_layer_leaves(int field, const void *values, unsigned log_n, void *l
 void p2o_fri_fold_layer(int field, const void *coeffs, unsigned log_n, unsigned arity_bits, const void *beta,
                         uint64_t shift_in, void *coeffs_out, void *values_out, uint64_t *shift_out);
 
+/* fri_proof_of_work (fri/prover.rs:136-188): smallest witness whose response has >= min_leading_zeros leading zeros.
+ * state: WIDTH canonical elements, input: the challenger's input_len (< 8) buffered elements.  0 = found. */
+int p2o_fri_pow(int field, const void *state, const void *input, unsigned input_len, unsigned min_leading_zeros,
+                uint64_t *witness);
+
 int p2o_max_threads(void);
 
 #ifdef __cplusplus

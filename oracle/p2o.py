@@ -77,6 +77,8 @@ def load(native: bool = False) -> ctypes.CDLL:
     lib.p2o_ext_w.argtypes = [ci]
     lib.p2o_ext_w.restype = u64
     lib.p2o_ext_mul.argtypes = [ci, vp, vp, vp]
+    lib.p2o_fri_pow.argtypes = [ci, vp, vp, ui, ui, ctypes.POINTER(u64)]
+    lib.p2o_fri_pow.restype = ci
     lib.p2o_fri_layer_leaves.argtypes = [ci, vp, ui, vp]
     lib.p2o_fri_fold_layer.argtypes = [ci, vp, ui, ui, vp, u64, vp, vp, ctypes.POINTER(u64)]
     _LIBS[native] = lib
@@ -260,3 +262,14 @@ def fri_committed_trees(field, coeffs, values, challenger, reduction_arity_bits,
     final = coeffs[: coeffs.shape[0] >> rate_bits].copy()
     challenger.observe_extension_elements(final)
     return trees, final
+
+
+def fri_pow(field, sponge_state, input_buffer, min_leading_zeros) -> int:
+    """fri_proof_of_work's search (:147-179): the smallest valid witness."""
+    st = np.ascontiguousarray(sponge_state, dtype=DTYPE[field])
+    inp = np.ascontiguousarray(input_buffer, dtype=DTYPE[field])
+    w = ctypes.c_uint64()
+    rc = load().p2o_fri_pow(field, st.ctypes.data, _p(inp), inp.size, min_leading_zeros, ctypes.byref(w))
+    if rc != 0:
+        raise ValueError("Proof of work failed. This is highly unlikely!")
+    return int(w.value)

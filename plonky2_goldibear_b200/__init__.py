@@ -8,10 +8,12 @@ from ._lib import Context, P2GError, library_path, load_library
 from .merkle_tree import MerkleTree, MerkleCap
 from .fri_oracle import PolynomialBatch, ProvingProcessInfo, SALT_SIZE
 from .challenger import Challenger
-from .fri_prover import FriConfig, FriParams, fri_committed_trees
+from .fri_prover import (FriConfig, FriParams, fri_committed_trees, fri_proof, fri_proof_of_work,
+                         fri_prover_query_rounds)
 
 __all__ = [
     "GOLDILOCKS", "BABYBEAR", "Field", "Context", "P2GError", "library_path", "load_library",
     "MerkleTree", "MerkleCap", "PolynomialBatch", "ProvingProcessInfo", "SALT_SIZE",
-    "Challenger", "FriConfig", "FriParams", "fri_committed_trees",
+    "Challenger", "FriConfig", "FriParams", "fri_committed_trees", "fri_proof", "fri_proof_of_work",
+    "fri_prover_query_rounds",
 ]

@@ -51,7 +51,7 @@ EXPORTS = [
     "p2g_release_workspace", "p2g_stream", "p2g_kernel_launches", "p2g_batch_get_rows", "p2g_batch_prove",
     "p2g_batch_download", "p2g_batch_shape", "p2g_batch_free", "p2g_dev_alloc", "p2g_dev_free", "p2g_ipc_export",
     "p2g_ipc_import", "p2g_ipc_close", "p2g_intt_allgather", "p2g_memcpy_async",
-    "p2g_fri_begin", "p2g_fri_commit_layer", "p2g_fri_fold", "p2g_fri_finish", "p2g_fri_shape", "p2g_fri_free",
+    "p2g_fri_begin", "p2g_fri_commit_layer", "p2g_fri_fold", "p2g_fri_finish", "p2g_fri_shape", "p2g_fri_free", "p2g_fri_pow",
 ]
 
 
@@ -135,6 +135,8 @@ def load_library() -> ctypes.CDLL:
         lib.p2g_fri_finish.restype = i32
         lib.p2g_fri_shape.argtypes = [vp, ctypes.POINTER(u32), ctypes.POINTER(u64)]
         lib.p2g_fri_shape.restype = i32
+        lib.p2g_fri_pow.argtypes = [vp, i32, i32, vp, vp, u32, u32, ctypes.POINTER(u64)]
+        lib.p2g_fri_pow.restype = i32
         lib.p2g_fri_free.argtypes = [vp, vp]
         lib.p2g_fri_free.restype = None
         _LIB = lib

@@ -148,6 +148,31 @@ __global__ void __launch_bounds__(128) permute_kernel(typename H::W *states, u64
     for (int i = 0; i < H::WIDTH; i++) states[t * H::WIDTH + i] = H::store(s[i]);
 }
 
+// ---- FRI grinding (fri_proof_of_work, plonky2/src/fri/prover.rs:136-188) ------------------------------------------
+// Candidate c = start + thread: overwrite lane `pos` of the half-duplexed sponge state with c, permute, and test the
+// LAST squeezed element (lane RATE-1, :175) for enough leading zeros as a canonical u64 (:176-177).  The smallest
+// hit of the launch wins (atomicMin): the reference takes whichever rayon finds first (find_any), any hit is a valid
+// witness, and "smallest" makes ours reproducible.
+template <class H>
+__global__ void __launch_bounds__(128) pow_search_kernel(const typename H::W *__restrict__ state, u32 pos, u32 min_leading_zeros,
+                                                         u64 start, u64 count, u64 last_candidate, unsigned long long *best) {
+    typedef typename H::W W;
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 cand = start + t;
+    const bool live = t < count && cand <= last_candidate && cand >= start;
+    W s[H::WIDTH];
+#pragma unroll
+    for (int i = 0; i < H::WIDTH; i++) s[i] = H::load(state[i]);
+#pragma unroll
+    for (int i = 0; i < H::RATE; i++)
+        if ((u32)i == pos) s[i] = H::load((W)(live ? cand : 0));
+    H::permute(s);
+    if (!live) return;
+    u64 resp = (u64)H::store(s[H::RATE - 1]);
+    u32 lz = resp ? (u32)__clzll((long long)resp) : 64u;
+    if (lz >= min_leading_zeros) atomicMin(best, (unsigned long long)cand);
+}
+
 // ---- device-resident accessors (MerkleTree::get / MerkleTree::prove on the GPU copy) -----------------------------
 template <class E>
 __global__ void gather_rows_kernel(const E *__restrict__ leaves, u64 pitch, u32 width, const u64 *__restrict__ idx,
@@ -253,6 +278,18 @@ void launch_permute(int field, int repr, void *states, uint64_t count, cudaStrea
         permute_t<HashBb<true>>(states, count, stream, launches);
     else
         permute_t<HashBb<false>>(states, count, stream, launches);
+}
+
+void launch_pow_search(int field, const void *state, uint32_t pos, uint32_t min_leading_zeros, uint64_t start,
+                       uint64_t count, uint64_t last_candidate, void *best, cudaStream_t stream, uint64_t *launches) {
+    unsigned blocks = (unsigned)((count + 127) / 128);
+    if (field == FIELD_GL)
+        pow_search_kernel<HashGl><<<blocks, 128, 0, stream>>>((const u64 *)state, pos, min_leading_zeros, start, count, last_candidate,
+                                                              (unsigned long long *)best);
+    else
+        pow_search_kernel<HashBb<false>><<<blocks, 128, 0, stream>>>((const u32 *)state, pos, min_leading_zeros, start, count,
+                                                                     last_candidate, (unsigned long long *)best);
+    ++*launches;
 }
 
 }  // namespace p2g

@@ -1189,6 +1189,47 @@ void p2g_fri_free(p2g_ctx *ctx, p2g_fri *s) {
     delete s;
 }
 
+// fri_proof_of_work (fri/prover.rs:136-188): the search only; the caller observes the witness afterwards (:181-186).
+int32_t p2g_fri_pow(p2g_ctx *ctx, int32_t field, int32_t hash, const void *sponge_state, const void *input_buffer,
+                    uint32_t input_len, uint32_t min_leading_zeros, uint64_t *witness_out) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const FieldInfo *fp;
+    int rc = check_field_hash(ctx, field, hash, &fp);
+    if (rc) return rc;
+    const FieldInfo &f = *fp;
+    if (!sponge_state || !witness_out || (input_len && !input_buffer)) return ctx->fail(P2G_ERR_INVALID, "NULL argument");
+    if (input_len >= 8) return ctx->fail(P2G_ERR_INVALID, "input_buffer holds %u elements: a Challenger never keeps a full rate", input_len);
+    const unsigned width = f.id == FIELD_GL ? 12 : 16;
+    // duplex_intermediate_state (:166-168): the sponge state with the buffered inputs written over its first lanes
+    unsigned char st_host[16 * 8];
+    memcpy(st_host, sponge_state, width * f.elem);
+    memcpy(st_host, input_buffer, input_len * f.elem);
+    if ((rc = ensure(ctx, ctx->misc, 256))) return rc;
+    unsigned char *dev = (unsigned char *)ctx->misc.ptr;
+    unsigned long long *best = (unsigned long long *)(dev + 128);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(dev, st_host, width * f.elem, cudaMemcpyHostToDevice, st));
+    const uint64_t last = (f.id == FIELD_GL ? P2G_GL_P : (uint64_t)P2G_BB_P) - 1;  // candidates run over 0..=F::neg_one() (:170)
+    const uint64_t batch = (uint64_t)1 << 22;
+    const unsigned long long none = ~0ull;
+    for (uint64_t start = 0; start <= last; start += batch) {
+        CK(cudaMemcpyAsync(best, &none, 8, cudaMemcpyHostToDevice, st));
+        uint64_t count = std::min<uint64_t>(batch, last - start + 1);
+        launch_pow_search(f.id, dev, input_len, min_leading_zeros, start, count, last, best, st, &ctx->launches);
+        unsigned long long got = none;
+        CK(cudaMemcpyAsync(&got, best, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (got != none) {
+            *witness_out = got;
+            return P2G_OK;
+        }
+        if (start + batch < start) break;
+    }
+    return ctx->fail(P2G_ERR_INVALID, "Proof of work failed. This is highly unlikely!");  // the reference's expect(), :179
+}
+
 int32_t p2g_permute(p2g_ctx *ctx, int32_t hash, int32_t repr, void *states, uint64_t count) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
     std::lock_guard<std::mutex> lock(ctx->mu);

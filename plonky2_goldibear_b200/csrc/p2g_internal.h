@@ -41,6 +41,11 @@ void launch_gather_proofs(const void *digests, uint32_t log_leaves, uint32_t cap
 // permutation of `count` states in place (device pointer)
 void launch_permute(int field, int repr, void *states, uint64_t count, cudaStream_t stream, uint64_t *launches);
 
+// FRI grinding: candidates [start, start + count) capped at last_candidate; *best (device u64, preset to ~0) receives the
+// smallest candidate whose response has >= min_leading_zeros leading zeros.  `state` = 12/16 canonical elements (device)
+void launch_pow_search(int field, const void *state, uint32_t pos, uint32_t min_leading_zeros, uint64_t start,
+                       uint64_t count, uint64_t last_candidate, void *best, cudaStream_t stream, uint64_t *launches);
+
 // ---- ntt.cu ------------------------------------------------------------------------------------
 struct NttPass {
     const void *src;

@@ -1,5 +1,5 @@
-"""Host mirror of the FRI commit phase, `fri_committed_trees` (plonky2/src/fri/prover.rs:83-133): same arguments, same
-return value (the layer trees and the final polynomial).  Per layer the CUDA library bit-reverses and chunks the
+"""Host mirror of the FRI prover, plonky2/src/fri/prover.rs: `fri_proof` (:22-77) = `fri_committed_trees` (:83-133) +
+`fri_proof_of_work` (:136-188) + `fri_prover_query_rounds` (:190-255), same arguments and return values.  Per layer the CUDA library bit-reverses and chunks the
 evaluations into a leaf matrix, builds its Merkle tree, folds the coefficients with the challenge and runs the coset
 NTT of the folded polynomial (p2g_fri_*); the Fiat-Shamir challenger runs here, between the two calls, exactly where
 the reference has it.  The layer trees stay on the GPU (`DeviceMerkleTree`) and serve the query phase
@@ -17,9 +17,11 @@ from .merkle_tree import DeviceMerkleTree, MerkleCap
 
 @dataclass
 class FriConfig:
-    """fri/mod.rs FriConfig: the two members the commit phase reads."""
+    """fri/mod.rs FriConfig: the members the prover reads."""
     rate_bits: int
     cap_height: int
+    proof_of_work_bits: int = 16
+    num_query_rounds: int = 28
 
 
 @dataclass
@@ -70,3 +72,60 @@ def fri_committed_trees(field: Field, coeffs, values, challenger, fri_params: Fr
         ctx.lib.p2g_fri_free(ctx.handle, state)
     challenger.observe_extension_elements(final)
     return trees, final
+
+
+def fri_proof_of_work(field: Field, challenger, config: FriConfig, ctx=None) -> int:
+    """fri_proof_of_work (:136-188): grind on the GPU (p2g_fri_pow), then observe the witness and re-check the
+    response through the ordinary challenger exactly as the reference does (:181-186)."""
+    ctx = ctx or _lib.default_context()
+    min_leading_zeros = config.proof_of_work_bits + (64 - field.order.bit_length())
+    state = np.ascontiguousarray(challenger.sponge_state, dtype=field.dtype)
+    inp = np.ascontiguousarray(np.array(challenger.input_buffer, dtype=field.dtype))
+    witness = ctypes.c_uint64()
+    ctx.check(ctx.lib.p2g_fri_pow(ctx.handle, field.field_id, field.hash_id, state.ctypes.data,
+                                  inp.ctypes.data if inp.size else None, inp.size, min_leading_zeros, ctypes.byref(witness)))
+    challenger.observe_element(witness.value)
+    pow_response = challenger.get_challenge()
+    assert 64 - int(pow_response).bit_length() >= min_leading_zeros
+    return int(witness.value)
+
+
+def fri_prover_query_rounds(initial_merkle_trees, trees, challenger, n: int, fri_params: FriParams):
+    """fri_prover_query_rounds / fri_prover_query_round (:190-255).  All rounds' rows and Merkle paths of one tree are
+    fetched with one gather launch each (the trees live on the GPU).  Returns, per round,
+    {"x_index", "initial_trees_proof": [(leaf row, siblings)], "steps": [(evals [arity][D], siblings)]}."""
+    indices = [int(r) % n for r in challenger.get_n_challenges(fri_params.config.num_query_rounds)]
+    rounds = [{"x_index": x, "initial_trees_proof": [], "steps": []} for x in indices]
+    for t in initial_merkle_trees:
+        rows, proofs = _get_and_prove(t, indices)
+        for rd, row, pr in zip(rounds, rows, proofs):
+            rd["initial_trees_proof"].append((row, pr))
+    cur = list(indices)
+    for i, tree in enumerate(trees):
+        arity_bits = fri_params.reduction_arity_bits[i]
+        cur = [x >> arity_bits for x in cur]
+        rows, proofs = _get_and_prove(tree, cur)
+        for rd, row, pr in zip(rounds, rows, proofs):
+            rd["steps"].append((np.asarray(row).reshape(1 << arity_bits, -1), pr))  # unflatten
+    return rounds
+
+
+def _get_and_prove(tree, indices):
+    if hasattr(tree, "get_many"):
+        return tree.get_many(indices), tree.prove_many(indices)
+    return [tree.get(i) for i in indices], [tree.prove(i) for i in indices]
+
+
+def fri_proof(field: Field, initial_merkle_trees, lde_polynomial_coeffs, lde_polynomial_values, challenger, fri_params: FriParams,
+              ctx=None, repr: int = REPR_CANONICAL):
+    """fri_proof (:22-77): {"commit_phase_merkle_caps", "query_round_proofs", "final_poly", "pow_witness"}."""
+    n = np.asarray(lde_polynomial_values).shape[0]
+    assert np.asarray(lde_polynomial_coeffs).shape[0] == n
+    trees, final_coeffs = fri_committed_trees(field, lde_polynomial_coeffs, lde_polynomial_values, challenger, fri_params, ctx=ctx, repr=repr)
+    pow_witness = fri_proof_of_work(field, challenger, fri_params.config, ctx=ctx)
+    rounds = fri_prover_query_rounds(initial_merkle_trees, trees, challenger, n, fri_params)
+    proof = {"commit_phase_merkle_caps": [t.cap for t in trees], "query_round_proofs": rounds, "final_poly": final_coeffs,
+             "pow_witness": pow_witness}
+    for t in trees:
+        t.free()
+    return proof

@@ -163,6 +163,56 @@ def test_oracle_commit_phase_passes_the_pinned_verifier_fold_checks(oracle, arit
             chk.fri_fold_chain(3, tag(values[chk.reverse_bits(3, lde_bits)]), steps, arities, bad, [tag(e) for e in final], lde_bits, 7, two_adic)
 
 
+def leading_zeros64(x):
+    return 64 - int(x).bit_length()
+
+
+@pytest.mark.parametrize("field,bits", [(0, 6), (0, 10), (1, 6), (1, 9)])
+def test_oracle_grinding_returns_the_smallest_valid_witness(oracle, field, bits):
+    import plonky2_goldibear_b200 as p2g
+    f = {0: p2g.GOLDILOCKS, 1: p2g.BABYBEAR}[field]
+    rng = np.random.default_rng(31 + bits)
+    min_lz = bits + (64 - f.order.bit_length())
+    for input_len in (0, 3, 7):
+        ch = oracle_challenger(oracle, f, field)
+        ch.observe_elements(rng.integers(0, f.order, size=16 + input_len, dtype=np.uint64))  # two duplexings, then input_len pending
+        assert len(ch.input_buffer) == input_len
+        w = oracle.fri_pow(field, ch.sponge_state, ch.input_buffer, min_lz)
+
+        def response(c):
+            s = ch.sponge_state.copy()
+            s[:input_len] = ch.input_buffer
+            s[input_len] = c
+            return int(oracle.permute(field, s)[7])
+        assert leading_zeros64(response(w)) >= min_lz
+        assert all(leading_zeros64(response(c)) < min_lz for c in range(w))
+        # and the ordinary challenger agrees with the half-duplex shortcut (prover.rs:181-186)
+        ch.observe_element(w)
+        assert leading_zeros64(ch.get_challenge()) >= min_lz
+
+
+def test_oracle_grinding_on_the_golden_transcript(oracle):
+    """At the point where the reference ground its proof of work (the frozen proof's transcript, replayed by the pinned
+    verifier code), the oracle's smallest witness is valid and not above the reference's (the reference keeps whichever
+    hit its thread pool finds first)."""
+    import json
+    import gl_fri_check as chk
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "gl_proof_fri.json")))
+    perm = lambda s: [int(x) for x in oracle.permute(0, np.array(s, dtype=np.uint64))]
+    two_adic = lambda bits: int(oracle.load().p2o_two_adic_generator(0, bits))
+    res = chk.verify(fx, perm, 7, two_adic)
+    min_lz = res["proof_of_work_bits"] + 0  # 64 - bits(order) = 0 for Goldilocks
+    w = oracle.fri_pow(0, res["pre_pow_state"], res["pre_pow_input"], min_lz)
+    assert w <= res["pow_witness"]
+    s = list(res["pre_pow_state"])
+    k = len(res["pre_pow_input"])
+    s[:k] = res["pre_pow_input"]
+    for cand in (w, res["pow_witness"]):
+        t = list(s)
+        t[k] = cand
+        assert leading_zeros64(perm(t)[7]) >= min_lz
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def gpu_fields():
     import plonky2_goldibear_b200 as p2g
@@ -282,3 +332,65 @@ def test_gpu_commit_phase_errors_are_the_reference_panics(ctx, oracle):
     ctx.lib.p2g_fri_free(ctx.handle, state)
     # wrong extension degree for the field
     assert ctx.lib.p2g_fri_begin(ctx.handle, 0, 0, 0, 4, 4, coeffs.ctypes.data, values.ctypes.data, 0, ctypes.byref(state)) == -5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("field,bits", [(0, 4), (0, 12), (0, 18), (1, 5), (1, 14)])
+def test_gpu_grinding_matches_oracle(ctx, oracle, field, bits):
+    import plonky2_goldibear_b200 as p2g
+    f = gpu_fields()[field]
+    rng = np.random.default_rng(bits)
+    for input_len in (0, 1, 7):
+        ch_o, ch_g = oracle_challenger(oracle, f, field), p2g.Challenger(f, ctx=ctx)
+        xs = rng.integers(0, f.order, size=8 + input_len, dtype=np.uint64)
+        ch_o.observe_elements(xs)
+        ch_g.observe_elements(xs)
+        exp = oracle.fri_pow(field, ch_o.sponge_state, ch_o.input_buffer, bits + 64 - f.order.bit_length())
+        got = p2g.fri_proof_of_work(f, ch_g, p2g.FriConfig(3, 4, proof_of_work_bits=bits), ctx=ctx)
+        assert got == exp
+        ch_o.observe_element(exp)
+        ch_o.get_challenge()
+        assert ch_o.get_challenge() == ch_g.get_challenge()
+
+
+@pytest.mark.gpu
+def test_gpu_fri_proof_is_accepted_by_the_pinned_verifier_checks(ctx, oracle):
+    """fri_proof end to end on the GPU (commit phase, grinding, query rounds served from device-resident trees), then the
+    verifier's side: transcript replay, proof-of-work check, Merkle paths against the caps, folding chain."""
+    import gl_fri_check as chk
+    import plonky2_goldibear_b200 as p2g
+    f = p2g.GOLDILOCKS
+    rng = np.random.default_rng(99)
+    degree_bits, rate_bits, cap_height, arities = 10, 3, 2, [4, 3, 1]
+    lde_bits = degree_bits + rate_bits
+    coeffs, values = lde_pair(rng, oracle, 0, degree_bits, rate_bits)
+    params = p2g.FriParams(p2g.FriConfig(rate_bits, cap_height, proof_of_work_bits=11, num_query_rounds=9), arities)
+    # one "initial" oracle: the codeword itself committed as a 2-column batch, kept on the device
+    initial = p2g.MerkleTree.new(f, oracle.fri_layer_leaves(0, values, 0), cap_height, ctx=ctx)
+    ch = p2g.Challenger(f, ctx=ctx)
+    ch.observe_cap(initial.cap)
+    proof = p2g.fri_proof(f, [initial], coeffs, values, ch, params, ctx=ctx)
+    # ---- verifier
+    vc = oracle_challenger(oracle, f, 0)
+    vc.observe_cap(initial.cap)
+    betas = []
+    for cap in proof["commit_phase_merkle_caps"]:
+        vc.observe_cap(cap)
+        betas.append(tuple(int(x) for x in vc.get_extension_challenge()))
+    vc.observe_extension_elements(proof["final_poly"])
+    vc.observe_element(proof["pow_witness"])
+    assert 64 - int(vc.get_challenge()).bit_length() >= 11
+    indices = [c % (1 << lde_bits) for c in vc.get_n_challenges(9)]
+    assert indices == [r["x_index"] for r in proof["query_round_proofs"]]
+    tag = lambda e: (int(e[0]), int(e[1]))
+    two_adic = lambda bits: int(oracle.load().p2o_two_adic_generator(0, bits))
+    for rd in proof["query_round_proofs"]:
+        x = rd["x_index"]
+        (row, path), = rd["initial_trees_proof"]
+        assert oracle.verify_merkle_proof_to_cap(0, row, x, initial.cap.hashes, path)
+        idx, steps = x, []
+        for (evals, path), cap, ab in zip(rd["steps"], proof["commit_phase_merkle_caps"], arities):
+            idx >>= ab
+            assert oracle.verify_merkle_proof_to_cap(0, evals.reshape(-1), idx, cap.hashes, path)
+            steps.append([tag(e) for e in evals])
+        chk.fri_fold_chain(x, tag(row), steps, arities, betas, [tag(e) for e in proof["final_poly"]], lde_bits, 7, two_adic)

@@ -173,6 +173,7 @@ def verify(fx, permute, generator, two_adic_generator):
     final_poly = [tuple(H(e)) for e in fx["final_poly"]]
     for e in final_poly:
         ch.observe_ext(e)
+    pre_pow = (list(ch.state), list(ch.inp))  # what fri_proof_of_work starts from (prover.rs:166-168)
     ch.observe(int(fx["pow_witness"], 16))
     pow_response = ch.challenge()
     assert pow_response < (1 << (64 - cfg["proof_of_work_bits"])), "proof of work (verifier.rs:48-60)"
@@ -208,4 +209,5 @@ def verify(fx, permute, generator, two_adic_generator):
         fri_fold_chain(x_index, total, [[tuple(H(e)) for e in step] for step in q["steps"]], arity_bits, fri_betas, final_poly,
                        lde_bits, generator, two_adic_generator)
         checked += 1
-    return {"queries_checked": checked, "query_indices": indices, "zeta": zeta}
+    return {"queries_checked": checked, "query_indices": indices, "zeta": zeta, "pre_pow_state": pre_pow[0], "pre_pow_input": pre_pow[1],
+            "pow_witness": int(fx["pow_witness"], 16), "proof_of_work_bits": cfg["proof_of_work_bits"]}
