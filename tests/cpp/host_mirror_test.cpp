@@ -6,6 +6,7 @@
 #include <random>
 
 #include "p2g/commit.hpp"
+#include "p2g/fri.hpp"
 #include "p2o.h"
 
 template <class F>
@@ -89,11 +90,82 @@ static int run(p2g::Context &ctx, int oracle_field, uint64_t order) {
     return 0;
 }
 
+// fri_committed_trees + fri_proof_of_work against the oracle's restatement, the transcript driven by the same
+// Challenger on both sides (its permutation runs on the GPU; parity of that permutation is checked elsewhere).
+template <class F>
+static int run_fri(p2g::Context &ctx, int oracle_field, uint64_t order) {
+    using E = typename F::Elem;
+    constexpr unsigned D = p2g::Ext<F>::D;
+    const unsigned degree_bits = 9, r = 3, h = 2, lde_bits = degree_bits + r;
+    const size_t n = size_t(1) << lde_bits;
+    std::mt19937_64 rng(77);
+    std::vector<E> coeffs(n * D, 0), values(n * D);
+    for (size_t i = 0; i < (size_t(1) << degree_bits) * D; i++) coeffs[i] = (E)(rng() % order);
+    for (unsigned k = 0; k < D; k++) {  // values = coset_fft(F::generator()) of each coordinate
+        std::vector<E> col(n);
+        for (size_t i = 0; i < n; i++) col[i] = coeffs[i * D + k];
+        p2o_coset_fft(oracle_field, col.data(), lde_bits, p2o_generator(oracle_field), 0);
+        for (size_t i = 0; i < n; i++) values[i * D + k] = col[i];
+    }
+    p2g::FriParams params{{r, h, 9, 4}, {4, 3, 1}};
+    p2g::Challenger<F> ch(ctx), ch_ref(ctx);
+    ch.observe_elements({1, 2, 3});
+    ch_ref.observe_elements({1, 2, 3});
+    auto got = p2g::fri_committed_trees<F>(ctx, coeffs, values, ch, params);
+    // oracle side, layer by layer
+    std::vector<E> oc = coeffs, ov = values;
+    uint64_t shift = p2o_generator(oracle_field);
+    unsigned lg = lde_bits;
+    CHECK(got.trees.size() == params.reduction_arity_bits.size());
+    for (size_t i = 0; i < params.reduction_arity_bits.size(); i++) {
+        unsigned a = (unsigned)params.reduction_arity_bits[i];
+        size_t rows = size_t(1) << (lg - a), width = (size_t)D << a;
+        std::vector<E> leaves(rows * width), digests(2 * (rows - (size_t(1) << h)) * F::NUM_HASH_OUT_ELTS), cap((size_t(1) << h) * F::NUM_HASH_OUT_ELTS);
+        p2o_fri_layer_leaves(oracle_field, ov.data(), lg, leaves.data());
+        CHECK(p2o_merkle_tree(oracle_field, leaves.data(), rows, width, h, digests.data(), cap.data(), 0) == 0);
+        CHECK(memcmp(got.trees[i].cap.hashes.data(), cap.data(), cap.size() * sizeof(E)) == 0);
+        CHECK(got.trees[i].download(0, leaves.size()) == leaves);
+        CHECK(got.trees[i].download(1, digests.size()) == digests);
+        auto row = got.trees[i].get(rows - 1);
+        CHECK(memcmp(row.data(), leaves.data() + (rows - 1) * width, width * sizeof(E)) == 0);
+        auto proof = got.trees[i].prove(rows - 1);
+        CHECK(p2o_verify_merkle_proof_to_cap(oracle_field, row.data(), width, rows - 1, cap.data(), h, proof.data(),
+                                             (unsigned)(proof.size() / F::NUM_HASH_OUT_ELTS)) == 1);
+        ch_ref.observe_elements(cap);
+        std::vector<E> beta = ch_ref.get_extension_challenge();
+        std::vector<E> nc((size_t(1) << (lg - a)) * D), nv(nc.size());
+        p2o_fri_fold_layer(oracle_field, oc.data(), lg, a, beta.data(), shift, nc.data(), nv.data(), &shift);
+        oc.swap(nc);
+        ov.swap(nv);
+        lg -= a;
+    }
+    oc.resize(((size_t(1) << lg) >> r) * D);
+    CHECK(got.final_coeffs == oc);
+    ch_ref.observe_elements(oc);
+    // grinding
+    uint64_t exp_w = 0;
+    CHECK(p2o_fri_pow(oracle_field, ch_ref.sponge_state.data(), ch_ref.input_buffer.data(), (unsigned)ch_ref.input_buffer.size(),
+                      (unsigned)(9 + (order >> 32 ? 0 : 33)), &exp_w) == 0);
+    CHECK((uint64_t)p2g::fri_proof_of_work<F>(ctx, ch, params.config) == exp_w);
+    // cap_height above the last layer's leaf count panics in the reference
+    bool threw = false;
+    try {
+        p2g::Challenger<F> c2(ctx);
+        p2g::fri_committed_trees<F>(ctx, coeffs, values, c2, p2g::FriParams{{r, 9, 9, 4}, {4}});
+    } catch (const std::invalid_argument &e) {
+        threw = strstr(e.what(), "cap_height=9 should be at most log2(leaves.len())=8") != nullptr;
+    }
+    CHECK(threw);
+    return 0;
+}
+
 int main() {
     try {
         p2g::Context ctx(0);
         if (run<p2g::Goldilocks>(ctx, P2O_FIELD_GL, 0xFFFFFFFF00000001ULL)) return 1;
         if (run<p2g::BabyBear>(ctx, P2O_FIELD_BB, 2013265921ULL)) return 1;
+        if (run_fri<p2g::Goldilocks>(ctx, P2O_FIELD_GL, 0xFFFFFFFF00000001ULL)) return 1;
+        if (run_fri<p2g::BabyBear>(ctx, P2O_FIELD_BB, 2013265921ULL)) return 1;
     } catch (const std::exception &e) {
         fprintf(stderr, "exception: %s\n", e.what());
         return 2;
