@@ -164,7 +164,9 @@ int32_t p2g_permute(p2g_ctx *ctx, int32_t hash, int32_t repr, void *states, uint
 /* Batched transforms on column-major data (parity tests for the NTT kernels; with P2G_FLAG_DEVICE_INPUT/OUTPUT the
  * column-sharded inverse transform of a multi-GPU commit):
  * kind 0: ifft (values -> coeffs, field/src/fft.rs:66-94); kind 1: coset LDE of coeffs with shift g and rate_bits,
- * output column-major natural order [num_cols][N] like lde_values (oracle.rs:125-150). */
+ * output column-major natural order [num_cols][N] like lde_values (oracle.rs:125-150); kind 2: coset_ifft with shift
+ * F::generator() (values on g*H -> coeffs, field/src/polynomial/mod.rs:62-72), the transform that ends
+ * compute_quotient_polys (plonk/prover.rs:921-925). */
 int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, uint32_t log_n, uint32_t num_cols,
                       uint32_t rate_bits, uint32_t flags, const void *in, void *out);
 
@@ -173,7 +175,10 @@ int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, u
  *
  *   p2g_fri_begin(coeffs, values)            lde_polynomial_coeffs / lde_polynomial_values, 2^log_n extension
  *                                            elements each, an element being its `degree` base coefficients in a
- *                                            row (F::Extension::as_base_slice); shift starts at F::generator() (:100)
+ *                                            row (F::Extension::as_base_slice); shift starts at F::generator() (:100).
+ *                                            values may be NULL: they are then computed on the device as
+ *                                            coeffs.coset_fft(F::generator()), which is how prove_openings obtains
+ *                                            them (fri/oracle.rs:226-231) -- no host FFT, no upload
  *   for arity_bits in reduction_arity_bits:
  *     p2g_fri_commit_layer(arity_bits, cap_height, cap_out, &tree)
  *                                            reverse_index_bits + chunks(arity) + flatten + MerkleTree::new (:103-110);

@@ -231,6 +231,18 @@ static void coset_fft(typename F::E *buf, unsigned lg_n, typename F::E shift, un
     fft_with_options<F>(buf, lg_n, zero_factor);
 }
 
+// coset_ifft, field/src/polynomial/mod.rs:62-72
+template <class F>
+static void coset_ifft(typename F::E *buf, unsigned lg_n, typename F::E shift) {
+    typedef typename F::E E;
+    ifft<F>(buf, lg_n);
+    E r = f_inv<F>(shift), pw = 1;
+    for (size_t j = 0; j < ((size_t)1 << lg_n); j++) {
+        buf[j] = F::mul(buf[j], pw);
+        pw = F::mul(pw, r);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Poseidon over Goldilocks, width 12: plonky2/src/hash/poseidon_goldilocks.rs
 // ------------------------------------------------------------------------------------------------
@@ -884,6 +896,12 @@ void p2o_coset_fft(int field, void *data, unsigned log_n, uint64_t shift, unsign
         coset_fft<GL>((uint64_t *)data, log_n, shift, zero_factor);
     else
         coset_fft<BB>((uint32_t *)data, log_n, (uint32_t)shift, zero_factor);
+}
+void p2o_coset_ifft(int field, void *data, unsigned log_n, uint64_t shift) {
+    if (field == P2O_FIELD_GL)
+        coset_ifft<GL>((uint64_t *)data, log_n, shift);
+    else
+        coset_ifft<BB>((uint32_t *)data, log_n, (uint32_t)shift);
 }
 void p2o_reverse_index_bits(void *data, size_t elem_bytes, unsigned log_n) {
     if (elem_bytes == 8)

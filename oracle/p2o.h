@@ -19,6 +19,8 @@
  *   plonky2/src/hash/poseidon_goldilocks.rs      Poseidon width 12 (naive :927-948, fast :889-922)
  *   plonky2/src/gates/poseidon2_babybear.rs:609-680,787-832,903-917  Poseidon2 width 16 (in-tree restatement
  *                                                of the external p3_poseidon2 permutation)
+ *   plonky2/src/fri/prover.rs:83-188             fri_committed_trees, fri_proof_of_work
+ *   plonky2/src/iop/challenger.rs                 (the transcript itself is host logic: plonky2_goldibear_b200/challenger.py)
  *
  * The reference is Rust and its field / Poseidon2 arithmetic lives in an un-vendored git dependency
  * (telosnetwork/Plonky3, branch goldilocks_improvements, no lockfile); there is no Rust toolchain in the
@@ -30,6 +32,9 @@
  *             order of from_values: the golden proof's Fiat-Shamir transcript and all 28 FRI query rounds re-verify
  *             with this oracle's permutation and constants (tools/gl_fri_check.py, tests/test_golden_fri.py), and
  *             fail with any other shift / root / leaf order.
+ *             FRI commit phase (bit reversal + chunking, fold order, shift^arity, extension W = 7): the oracle's layers
+ *             pass the same verifier fold checks that re-verify the golden proof (tests/test_fri_commit.py);
+ *             grinding: on the golden transcript the smallest witness is valid and <= the recorded pow_witness.
  *   unpinned: Poseidon2-BabyBear numeric output (no literal vector exists in the reference tree; only the
  *             structure is pinned by the in-tree restatement), BabyBear generator 31 and two-adic root
  *             0x1a427a41, Goldilocks two-adic roots of order above 2^17 (the 2^32 root 1753635133440165772 is the
@@ -69,6 +74,7 @@ void p2o_poseidon2_bb(uint32_t state[16]);
 void p2o_fft(int field, void *data, unsigned log_n, unsigned zero_factor); /* fft_with_options(.., Some(zero_factor), None) */
 void p2o_ifft(int field, void *data, unsigned log_n);                      /* ifft */
 void p2o_coset_fft(int field, void *data, unsigned log_n, uint64_t shift, unsigned zero_factor);
+void p2o_coset_ifft(int field, void *data, unsigned log_n, uint64_t shift); /* polynomial/mod.rs:62-72 */
 void p2o_reverse_index_bits(void *data, size_t elem_bytes, unsigned log_n);
 size_t p2o_reverse_bits(size_t x, unsigned num_bits);
 

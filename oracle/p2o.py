@@ -58,6 +58,7 @@ def load(native: bool = False) -> ctypes.CDLL:
     lib.p2o_fft.argtypes = [ci, vp, ui, ui]
     lib.p2o_ifft.argtypes = [ci, vp, ui]
     lib.p2o_coset_fft.argtypes = [ci, vp, ui, u64, ui]
+    lib.p2o_coset_ifft.argtypes = [ci, vp, ui, u64]
     lib.p2o_reverse_index_bits.argtypes = [vp, sz, ui]
     lib.p2o_reverse_bits.argtypes = [sz, ui]
     lib.p2o_reverse_bits.restype = sz
@@ -117,6 +118,12 @@ def coset_fft(field, col, shift, zero_factor=0):
     lib = load()
     a = np.ascontiguousarray(col, dtype=DTYPE[field]).copy()
     lib.p2o_coset_fft(field, a.ctypes.data, int(np.log2(a.size)), shift, zero_factor)
+    return a
+
+
+def coset_ifft(field, col, shift):
+    a = np.ascontiguousarray(col, dtype=DTYPE[field]).copy()
+    load().p2o_coset_ifft(field, a.ctypes.data, a.size.bit_length() - 1, int(shift))
     return a
 
 

@@ -7,6 +7,7 @@ from .fields import GOLDILOCKS, BABYBEAR, Field
 from ._lib import Context, P2GError, library_path, load_library
 from .merkle_tree import MerkleTree, MerkleCap
 from .fri_oracle import PolynomialBatch, ProvingProcessInfo, SALT_SIZE
+from . import polynomial
 from .challenger import Challenger
 from .fri_prover import (FriConfig, FriParams, fri_committed_trees, fri_proof, fri_proof_of_work,
                          fri_prover_query_rounds)
@@ -14,6 +15,6 @@ from .fri_prover import (FriConfig, FriParams, fri_committed_trees, fri_proof, f
 __all__ = [
     "GOLDILOCKS", "BABYBEAR", "Field", "Context", "P2GError", "library_path", "load_library",
     "MerkleTree", "MerkleCap", "PolynomialBatch", "ProvingProcessInfo", "SALT_SIZE",
-    "Challenger", "FriConfig", "FriParams", "fri_committed_trees", "fri_proof", "fri_proof_of_work",
+    "polynomial", "Challenger", "FriConfig", "FriParams", "fri_committed_trees", "fri_proof", "fri_proof_of_work",
     "fri_prover_query_rounds",
 ]

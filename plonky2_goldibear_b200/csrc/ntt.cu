@@ -501,4 +501,29 @@ void launch_leaves_to_columns(int field, const void *leaves, uint64_t pitch, uin
     ++*launches;
 }
 
+// data[c][j] *= base^j (base given as a three-level power table): the trailing step of coset_ifft
+// (field/src/polynomial/mod.rs:62-72), where base = shift^-1
+template <class F>
+__global__ void scale_powers_kernel(typename F::E *data, u32 log_n, u32 num_cols, u64 col_stride, const typename F::E *__restrict__ spow) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ((u64)num_cols << log_n)) return;
+    u32 j = (u32)(t & (((u64)1 << log_n) - 1));
+    u64 c = t >> log_n;
+    typename F::E *p = data + c * col_stride + j;
+    *p = F::store_user(F::mul(F::load_user(*p), pow3<F>(spow, j)));
+}
+
+void launch_scale_powers(int field, int repr, void *data, uint32_t log_n, uint32_t num_cols, uint64_t col_stride, const void *spow,
+                         cudaStream_t stream, uint64_t *launches) {
+    u64 total = ((u64)num_cols) << log_n;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    if (field == FIELD_GL)
+        scale_powers_kernel<NttGl><<<blocks, 256, 0, stream>>>((u64 *)data, log_n, num_cols, col_stride, (const u64 *)spow);
+    else if (repr)
+        scale_powers_kernel<NttBb<true>><<<blocks, 256, 0, stream>>>((u32 *)data, log_n, num_cols, col_stride, (const u32 *)spow);
+    else
+        scale_powers_kernel<NttBb<false>><<<blocks, 256, 0, stream>>>((u32 *)data, log_n, num_cols, col_stride, (const u32 *)spow);
+    ++*launches;
+}
+
 }  // namespace p2g

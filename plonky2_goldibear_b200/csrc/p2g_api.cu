@@ -986,7 +986,7 @@ int32_t p2g_fri_begin(p2g_ctx *ctx, int32_t field, int32_t hash, int32_t repr_in
     if (degree != ext_degree(f))
         return ctx->fail(P2G_ERR_UNSUPPORTED, "extension degree %u: the GPU path has D = 2 for Goldilocks and D = 4 for BabyBear", degree);
     if (log_n > f.two_adicity || log_n > 30) return ctx->fail(P2G_ERR_INVALID, "codeword length 2^%u exceeds the field's two-adicity", log_n);
-    if (!coeffs || !values) return ctx->fail(P2G_ERR_INVALID, "coeffs / values is NULL");
+    if (!coeffs) return ctx->fail(P2G_ERR_INVALID, "coeffs is NULL");
     const uint64_t n = (uint64_t)1 << log_n;
     const size_t bytes = (size_t)n * degree * f.elem;
     const bool dev_in = flags & P2G_FLAG_DEVICE_INPUT;
@@ -1021,12 +1021,21 @@ int32_t p2g_fri_begin(p2g_ctx *ctx, int32_t field, int32_t hash, int32_t repr_in
         src = ctx->in.ptr;
     }
     launch_fri_split(f.id, src, n, s->coeffs, st, &ctx->launches);
-    src = values;
-    if (!dev_in) {
-        CK(cudaMemcpyAsync(ctx->in.ptr, values, bytes, cudaMemcpyHostToDevice, st));
-        src = ctx->in.ptr;
+    if (values) {
+        src = values;
+        if (!dev_in) {
+            CK(cudaMemcpyAsync(ctx->in.ptr, values, bytes, cudaMemcpyHostToDevice, st));
+            src = ctx->in.ptr;
+        }
+        launch_fri_bitrev16(src, log_n, s->values, st, &ctx->launches);  // reverse_index_bits_in_place, prover.rs:103
+    } else if (log_n == 0) {
+        CK(cudaMemcpyAsync(s->values, src, bytes, cudaMemcpyDeviceToDevice, st));
+    } else {
+        // lde_polynomial_values = lde_polynomial_coeffs.coset_fft(F::generator()) (fri/oracle.rs:226-231), computed here,
+        // straight into bit-reversed order
+        if (log_n > MAX_TILE_LOG && (rc = ensure(ctx, ctx->tmp, bytes))) return rc;
+        if ((rc = run_transform(ctx, f, repr, false, log_n, degree, s->coeffs, ctx->tmp.ptr, s->values, degree, f.generator, 0))) return rc;
     }
-    launch_fri_bitrev16(src, log_n, s->values, st, &ctx->launches);  // reverse_index_bits_in_place, prover.rs:103
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     guard.s = nullptr;
@@ -1258,7 +1267,7 @@ int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, u
     const FieldInfo &f = field == P2G_FIELD_GOLDILOCKS ? kGl : kBb;
     if (f.id == FIELD_GL) repr = 0;
     if (!num_cols || !in || !out) return ctx->fail(P2G_ERR_INVALID, "empty transform");
-    if (kind == 0) rate_bits = 0;
+    if (kind == 0 || kind == 2) rate_bits = 0;
     if (log_n + rate_bits > f.two_adicity || log_n + rate_bits > 30 || log_n > 3 * MAX_TILE_LOG) return ctx->fail(P2G_ERR_INVALID, "transform size unsupported");
     const bool dev_in = flags & P2G_FLAG_DEVICE_INPUT, dev_out = flags & P2G_FLAG_DEVICE_OUTPUT;
     const uint64_t n = (uint64_t)1 << log_n, N = n << rate_bits;
@@ -1267,13 +1276,20 @@ int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, u
     int rc;
     if ((rc = ensure(ctx, ctx->in, in_bytes))) return rc;
     CK(cudaMemcpyAsync(ctx->in.ptr, in, in_bytes, dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-    if (kind == 0) {
+    if (kind == 0 || kind == 2) {
         void *dst = out;
         if (!dev_out) {
             if ((rc = ensure(ctx, ctx->coeffs, in_bytes))) return rc;
             dst = ctx->coeffs.ptr;
         }
         if ((rc = run_transform(ctx, f, repr, true, log_n, num_cols, ctx->in.ptr, nullptr, dst, n, 0, 0))) return rc;
+        if (kind == 2) {
+            // coset_ifft (polynomial/mod.rs:62-72): coefficient j of the plain inverse transform times shift^-j
+            const void *spow;
+            if ((rc = get_pow_table(ctx, f, f_inv(f, f.generator), &spow))) return rc;
+            launch_scale_powers(f.id, repr, dst, log_n, num_cols, n, spow, st, &ctx->launches);
+            CK(cudaGetLastError());
+        }
         if (!dev_out) CK(cudaMemcpyAsync(out, dst, in_bytes, cudaMemcpyDeviceToHost, st));
     } else if (kind == 1) {
         size_t out_bytes = (size_t)num_cols * N * f.elem;

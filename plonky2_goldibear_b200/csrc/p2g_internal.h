@@ -88,6 +88,10 @@ void launch_salt_scatter(int field, const void *salts, uint32_t num_salt, uint32
 void launch_leaves_to_columns(int field, const void *leaves, uint64_t pitch, uint32_t num_cols, uint32_t log_N,
                               void *out, cudaStream_t stream, uint64_t *launches);
 
+// data[c][j] *= base^j for j < 2^log_n (caller's representation in and out); spow = three-level power table of base
+void launch_scale_powers(int field, int repr, void *data, uint32_t log_n, uint32_t num_cols, uint64_t col_stride, const void *spow,
+                         cudaStream_t stream, uint64_t *launches);
+
 // ---- fri.cu ------------------------------------------------------------------------------------
 // out[i] = in[bitrev(i)], 16-byte elements (one extension element: 2 x u64 or 4 x u32)
 void launch_fri_bitrev16(const void *in, uint32_t log_n, void *out, cudaStream_t stream, uint64_t *launches);

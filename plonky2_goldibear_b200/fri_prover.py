@@ -32,13 +32,16 @@ class FriParams:
 
 
 def fri_committed_trees(field: Field, coeffs, values, challenger, fri_params: FriParams, ctx=None, repr: int = REPR_CANONICAL):
-    """coeffs, values: [n][D] arrays (lde_polynomial_coeffs / lde_polynomial_values as base-field slices).
+    """coeffs, values: [n][D] arrays (lde_polynomial_coeffs / lde_polynomial_values as base-field slices); values may be
+    None, in which case the library computes them as coeffs.coset_fft(F::generator()) on the device (what
+    prove_openings does on the CPU, fri/oracle.rs:226-231).
     Returns (trees, final_coeffs) like the reference; `challenger` is advanced exactly as the reference advances it."""
     ctx = ctx or _lib.default_context()
     d = field.extension_degree
     coeffs = np.ascontiguousarray(np.asarray(coeffs, dtype=field.dtype))
-    values = np.ascontiguousarray(np.asarray(values, dtype=field.dtype))
-    if coeffs.ndim != 2 or coeffs.shape[1] != d or values.shape != coeffs.shape:
+    if values is not None:
+        values = np.ascontiguousarray(np.asarray(values, dtype=field.dtype))
+    if coeffs.ndim != 2 or coeffs.shape[1] != d or (values is not None and values.shape != coeffs.shape):
         raise ValueError("coeffs and values must both be [n][%d] arrays" % d)
     n = coeffs.shape[0]
     if n <= 0 or n & (n - 1):
@@ -46,7 +49,7 @@ def fri_committed_trees(field: Field, coeffs, values, challenger, fri_params: Fr
     log_n = n.bit_length() - 1
     state = ctypes.c_void_p()
     ctx.check(ctx.lib.p2g_fri_begin(ctx.handle, field.field_id, field.hash_id, repr, d, log_n, coeffs.ctypes.data,
-                                    values.ctypes.data, 0, ctypes.byref(state)))
+                                    values.ctypes.data if values is not None else None, 0, ctypes.byref(state)))
     trees = []
     try:
         for arity_bits in fri_params.reduction_arity_bits:
@@ -119,8 +122,8 @@ def _get_and_prove(tree, indices):
 def fri_proof(field: Field, initial_merkle_trees, lde_polynomial_coeffs, lde_polynomial_values, challenger, fri_params: FriParams,
               ctx=None, repr: int = REPR_CANONICAL):
     """fri_proof (:22-77): {"commit_phase_merkle_caps", "query_round_proofs", "final_poly", "pow_witness"}."""
-    n = np.asarray(lde_polynomial_values).shape[0]
-    assert np.asarray(lde_polynomial_coeffs).shape[0] == n
+    n = np.asarray(lde_polynomial_coeffs).shape[0]
+    assert lde_polynomial_values is None or np.asarray(lde_polynomial_values).shape[0] == n
     trees, final_coeffs = fri_committed_trees(field, lde_polynomial_coeffs, lde_polynomial_values, challenger, fri_params, ctx=ctx, repr=repr)
     pow_witness = fri_proof_of_work(field, challenger, fri_params.config, ctx=ctx)
     rounds = fri_prover_query_rounds(initial_merkle_trees, trees, challenger, n, fri_params)

@@ -394,3 +394,47 @@ def test_gpu_fri_proof_is_accepted_by_the_pinned_verifier_checks(ctx, oracle):
             assert oracle.verify_merkle_proof_to_cap(0, evals.reshape(-1), idx, cap.hashes, path)
             steps.append([tag(e) for e in evals])
         chk.fri_fold_chain(x, tag(row), steps, arities, betas, [tag(e) for e in proof["final_poly"]], lde_bits, 7, two_adic)
+
+
+# ---- the transforms around the quotient stage and prove_openings ------------------------------------
+@pytest.mark.parametrize("field", [0, 1])
+def test_oracle_coset_ifft_inverts_coset_fft(oracle, field):
+    rng = np.random.default_rng(8)
+    g = int(oracle.load().p2o_generator(field))
+    for log_n in (0, 1, 5, 9):
+        coeffs = rng.integers(0, oracle.ORDER[field], size=1 << log_n, dtype=np.uint64).astype(oracle.DTYPE[field])
+        vals = oracle.coset_fft(field, coeffs, g)
+        assert (oracle.coset_ifft(field, vals, g) == coeffs).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("field,log_n,cols", [(0, 0, 1), (0, 3, 2), (0, 10, 16), (0, 13, 5), (0, 21, 2), (1, 4, 3), (1, 12, 48), (1, 22, 1)])
+def test_gpu_coset_ifft_matches_oracle(ctx, oracle, field, log_n, cols):
+    import plonky2_goldibear_b200 as p2g
+    f = gpu_fields()[field]
+    rng = np.random.default_rng(log_n)
+    vals = rng.integers(0, f.order, size=(cols, 1 << log_n), dtype=np.uint64).astype(f.dtype)
+    got = p2g.polynomial.coset_ifft(f, vals, ctx=ctx)
+    for j in range(cols):
+        assert (got[j] == oracle.coset_ifft(field, vals[j], f.generator)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("field,degree_bits,rate_bits,arities", [(0, 9, 3, [4, 4]), (0, 13, 1, [3, 2]), (0, 3, 0, [1]), (1, 10, 3, [4, 3])])
+def test_gpu_commit_phase_computes_the_lde_values_itself(ctx, oracle, field, degree_bits, rate_bits, arities):
+    """prove_openings hands fri_proof `lde_final_poly.coset_fft(g)` (fri/oracle.rs:226-231); with values=None the library
+    computes that codeword on the device and the result equals the run fed with the oracle's values."""
+    import plonky2_goldibear_b200 as p2g
+    f = gpu_fields()[field]
+    rng = np.random.default_rng(4)
+    coeffs, values = lde_pair(rng, oracle, field, degree_bits, rate_bits)
+    params = p2g.FriParams(p2g.FriConfig(rate_bits, 1), arities)
+    ch_a, ch_b = p2g.Challenger(f, ctx=ctx), p2g.Challenger(f, ctx=ctx)
+    trees_a, final_a = p2g.fri_committed_trees(f, coeffs, values, ch_a, params, ctx=ctx)
+    trees_b, final_b = p2g.fri_committed_trees(f, coeffs, None, ch_b, params, ctx=ctx)
+    assert (final_a == final_b).all() and ch_a.get_challenge() == ch_b.get_challenge()
+    for a, b in zip(trees_a, trees_b):
+        assert (a.cap.hashes == b.cap.hashes).all()
+        assert (a.download("leaves") == b.download("leaves")).all()
+        a.free()
+        b.free()
