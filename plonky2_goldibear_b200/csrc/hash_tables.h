@@ -5,7 +5,10 @@
 namespace p2g {
 
 struct PoseidonGlTables {
-    unsigned long long rc[31][12];  // rc[r] = ALL_ROUND_CONSTANTS[12r..12r+12] (poseidon_goldilocks.rs:114-212), rc[30] = 0
+    unsigned long long rc0[12];     // ALL_ROUND_CONSTANTS[0..12] (poseidon_goldilocks.rs:114-212), added before round 0
+    // constants of rounds 1..29 (and zeros for "round 30") split into the MDS layer's three limbs, bits 0-21 / 22-43 / 44-63:
+    // rcl[r][k][i] = limb k of ALL_ROUND_CONSTANTS[12 r + i]; the MDS of round r-1 adds rcl[r]
+    unsigned int rcl[31][3][12];
 };
 
 struct Poseidon2BbTables {

@@ -3,7 +3,7 @@
 // Replaces the reference's CPU permutation plonky2/src/hash/poseidon_goldilocks.rs:912-922 (same function as its
 // plain form :927-948: constant layer :519-535, S-box :746-760, MDS :547-557).
 // Differences that do not change a single output bit:
-//   * the MDS layer works on the 32-bit halves of the state with shifts and adds only (pgl_circ_half) and folds the
+//   * the MDS layer works on three 22-bit limbs of the state with shifts and adds only (pgl_circ_limb) and folds the
 //     NEXT round's constants into its sums (the reference adds them at the top of a round);
 //   * the partial rounds use the plain form (S-box on lane 0, full MDS) rather than the sparse-factor form;
 //   * state words are kept as arbitrary u64 representatives and made canonical only when a digest is stored.
@@ -24,7 +24,7 @@ __device__ __forceinline__ u64 pgl_sbox(u64 x) {
     return gl_mul(x3, x4);
 }
 
-// acc_lo + acc_hi * 2^32 (both < 2^42: sums of twelve 32-bit halves times constants <= 41, plus a constant half)
+// acc_lo + acc_hi * 2^32 (acc_lo < 2^53, acc_hi < 2^43: the reassembled limbs of one MDS output)
 // -> representative.  With acc_hi = ah1*2^32 + ah0:  v = acc_lo + ah1*EPS + ah0*2^32  (2^64 = EPS); the first two
 // terms cannot overflow, the last add can carry once, and that carry folds back in as +EPS without a second carry.
 __device__ __forceinline__ u64 pgl_fold(u64 acc_lo, u64 acc_hi) {
@@ -46,48 +46,49 @@ __device__ __forceinline__ u64 pgl_fold(u64 acc_lo, u64 acc_hi) {
     return gl_pack(w0, w1);
 }
 
-// Circulant part of the MDS layer on one 32-bit half of the state: y[r] = sum_i circ[i] * x[(i + r) % 12] with
+// Circulant part of the MDS layer on one 22-bit LIMB of the state: y[r] = sum_i circ[i] * x[(i + r) % 12] (+ add[r]) with
 // circ = (17,15,41,16,2,28,13,13,39,18,34,20) (poseidon_goldilocks.rs:301), computed WITHOUT multiplications.
-// The direct product needs 144 IMAD.WIDE per half (2.6 issue cycles each on B200 against 1.4 for an add); instead the length-12
-// cyclic correlation is split as 12 = 3 x 4: a 4-point DFT along t of x[j + 3t] (integers and Gaussian integers,
-// adds only), three 3-point "twisted" cyclic products modulo z^3 - lambda (lambda = 1, i, -1; the fourth is the
-// conjugate of the second because the input is real) against the transformed circulant, and the inverse 4-point DFT.
-// The transformed circulant, with the 1/4 (and 1/2 for the complex pair) of the inverse folded in, is all small:
+// The direct product needs 144 IMAD.WIDE per 32-bit half; instead the length-12 cyclic correlation is split as
+// 12 = 3 x 4: a 4-point DFT along t of x[j + 3t] (integers and Gaussian integers, adds only), three 3-point "twisted"
+// cyclic products modulo z^3 - lambda (lambda = 1, i, -1; the fourth is the conjugate of the second because the input
+// is real) against the transformed circulant, and the inverse 4-point DFT.  The transformed circulant, with the 1/4
+// (and 1/2 for the complex pair) of the inverse folded in, is all small:
 //   f=0: (16, 32, 16)   f=2: (-1, -8, 2)   f=1: (2+i, -4-i, 16-i)
-// so every product is a shift, an add or a negation on 64-bit signed integers (values stay below 2^42).
-// The reference reaches the same product through winterfell's mds_multiply_freq (:956-1088); this derivation and its
-// constants were re-done from the circulant and checked against the direct product (tests: Poseidon known answers).
-__device__ __forceinline__ void pgl_circ_half(const u32 x[12], long long y[12], const long long add[12]) {
-    long long f0[3], f2[3], re[3], im[3];
+// so every product is a shift, an add or a negation.  The reference reaches the same product through
+// mds_multiply_freq (:956-1088); this derivation and its constants were re-done from the circulant and checked against
+// the direct product (tests: Poseidon known answers).
+// Arithmetic is plain 32-bit wrap-around: inputs < 2^22, outputs < 264 * 2^22 < 2^31, intermediates may wrap (every
+// operation is a ring operation mod 2^32 and the true result fits).  There are no carries, so each add / shift-add can
+// issue on either integer pipe (IADD3 / LEA on the half-rate ALU pipe, IMAD.IADD / IMAD on the FMA pipe) and ptxas
+// balances them; an earlier formulation on 32-bit halves with 64-bit accumulators kept its carry chains on the ALU pipe
+// (ncu: ALU 82% busy, FMA 30%) and was 17% slower per layer (profiles/r1_leaf_sponge_cost_model.json).
+__device__ __forceinline__ void pgl_circ_limb(const u32 x[12], u32 y[12], const u32 add[12]) {
+    u32 f0[3], f2[3], re[3], im[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        long long x0 = x[j], x1 = x[j + 3], x2 = x[j + 6], x3 = x[j + 9];
-        long long p02 = x0 + x2, p13 = x1 + x3;
+        u32 x0 = x[j], x1 = x[j + 3], x2 = x[j + 6], x3 = x[j + 9];
+        u32 p02 = x0 + x2, p13 = x1 + x3;
         f0[j] = p02 + p13;
         f2[j] = p02 - p13;
         re[j] = x0 - x2;
         im[j] = x1 - x3;
     }
-    // f = 0 (lambda = 1), constants (16, 32, 16):  Y0 = 16 * (s + a2, s + a0, s + a1)
-    long long s = f0[0] + f0[1] + f0[2];
-    long long y0[3] = {(s + f0[2]) << 4, (s + f0[0]) << 4, (s + f0[1]) << 4};
-    // f = 2 (lambda = -1), constants (-1, -8, 2)
-    long long y2[3] = {(f2[2] << 3) - f2[0] - (f2[1] << 1), -(f2[0] << 3) - f2[1] - (f2[2] << 1), (f2[0] << 1) - (f2[1] << 3) - f2[2]};
-    // f = 1 (lambda = i), constants b0 = 2+i, b1 = -4-i, b2 = 16-i;  a*(br + i*bi) = (r*br - i*bi) + i*(r*bi + i*br)
-    long long r0 = re[0], i0 = im[0], r1 = re[1], i1 = im[1], r2 = re[2], i2 = im[2];
-    // T = a1*b2 + a2*b1
-    long long t_re = (r1 << 4) + i1 - (r2 << 2) + i2;
-    long long t_im = (i1 << 4) - r1 - r2 - (i2 << 2);
-    long long y1r[3], y1i[3];
-    y1r[0] = (r0 << 1) - i0 - t_im;                       // a0*b0 + i*T
+    u32 s = f0[0] + f0[1] + f0[2];
+    u32 y0[3] = {(s + f0[2]) << 4, (s + f0[0]) << 4, (s + f0[1]) << 4};
+    u32 y2[3] = {(f2[2] << 3) - f2[0] - (f2[1] << 1), 0u - (f2[0] << 3) - f2[1] - (f2[2] << 1), (f2[0] << 1) - (f2[1] << 3) - f2[2]};
+    u32 r0 = re[0], i0 = im[0], r1 = re[1], i1 = im[1], r2 = re[2], i2 = im[2];
+    u32 t_re = (r1 << 4) + i1 - (r2 << 2) + i2;
+    u32 t_im = (i1 << 4) - r1 - r2 - (i2 << 2);
+    u32 y1r[3], y1i[3];
+    y1r[0] = (r0 << 1) - i0 - t_im;
     y1i[0] = r0 + (i0 << 1) + t_re;
-    y1r[1] = i0 - (r0 << 2) + (r1 << 1) - i1 + r2 - (i2 << 4);   // a0*b1 + a1*b0 + i*a2*b2
+    y1r[1] = i0 - (r0 << 2) + (r1 << 1) - i1 + r2 - (i2 << 4);
     y1i[1] = r1 - r0 - (i0 << 2) + (i1 << 1) + (r2 << 4) + i2;
-    y1r[2] = (r0 << 4) + i0 - (r1 << 2) + i1 + (r2 << 1) - i2;   // a0*b2 + a1*b1 + a2*b0
+    y1r[2] = (r0 << 4) + i0 - (r1 << 2) + i1 + (r2 << 1) - i2;
     y1i[2] = (i0 << 4) - r0 - r1 - (i1 << 2) + r2 + (i2 << 1);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        long long p = y0[j] + y2[j], m = y0[j] - y2[j];
+        u32 p = y0[j] + y2[j], m = y0[j] - y2[j];
         y[j] = p + y1r[j] + add[j];
         y[j + 3] = m + y1i[j] + add[j + 3];
         y[j + 6] = p - y1r[j] + add[j + 6];
@@ -95,30 +96,39 @@ __device__ __forceinline__ void pgl_circ_half(const u32 x[12], long long y[12], 
     }
 }
 
-// out = MDS * s (+ next round constants).  MDS = circ(17,15,41,16,2,28,13,13,39,18,34,20) + diag(8,0,...)
-// (poseidon_goldilocks.rs:301-302; row r of the product is sum_i circ[i] * s[(i+r)%12], :547-557).
-template <bool ADD_CONST>
-__device__ __forceinline__ void pgl_mds(u64 s[12], const u64 *next_rc) {
-    u32 lo[12], hi[12];
+// out = MDS * s + next round constants.  MDS = circ(17,15,41,16,2,28,13,13,39,18,34,20) + diag(8,0,...)
+// (poseidon_goldilocks.rs:301-302; row r of the product is sum_i circ[i] * s[(i+r)%12], :547-557), applied to three
+// limbs (22 + 22 + 20 bits) of every lane; out = l0 + l1 * 2^22 + l2 * 2^44 is reassembled with two IMAD.WIDE into the
+// (acc_lo, acc_hi) pair pgl_fold takes:  acc_lo = l1 * 2^22 + l0 (< 2^53),  acc_hi = l2 * 2^12 (< 2^43).
+// rcl = the next round's constants pre-split into the same limbs (hash_tables.h); they and the diagonal term ride as
+// third addends of the last adds.
+__device__ __forceinline__ void pgl_mds(u64 s[12], const u32 (*rcl)[12]) {
+    u32 l0[12], l1[12], l2[12], c0[12], c1[12], c2[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-        lo[i] = (u32)s[i];
-        hi[i] = (u32)(s[i] >> 32);
+        u32 lo = (u32)s[i], hi = (u32)(s[i] >> 32);
+        l0[i] = lo & 0x3fffffu;
+        l1[i] = __funnelshift_r(lo, hi, 22) & 0x3fffffu;
+        l2[i] = hi >> 12;
+        c0[i] = rcl[0][i];
+        c1[i] = rcl[1][i];
+        c2[i] = rcl[2][i];
     }
-    long long yl[12], yh[12], cl[12], ch[12];
+    c0[0] += l0[0] << 3;  // the diagonal entry 8
+    c1[0] += l1[0] << 3;
+    c2[0] += l2[0] << 3;
+    u32 y0[12], y1[12], y2[12];
+    pgl_circ_limb(l0, y0, c0);
+    pgl_circ_limb(l1, y1, c1);
+    pgl_circ_limb(l2, y2, c2);
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        u64 c = ADD_CONST ? next_rc[r] : 0;
-        cl[r] = (long long)(u32)c;
-        ch[r] = (long long)(c >> 32);
+        u64 al = (u64)y1[r] * 0x400000u + y0[r];
+        u64 ah = (u64)y2[r] * 0x1000u;
+        s[r] = pgl_fold(al, ah);
     }
-    cl[0] += (long long)lo[0] << 3;  // the diagonal entry 8
-    ch[0] += (long long)hi[0] << 3;
-    pgl_circ_half(lo, yl, cl);
-    pgl_circ_half(hi, yh, ch);
-#pragma unroll
-    for (int r = 0; r < 12; r++) s[r] = pgl_fold((u64)yl[r], (u64)yh[r]);
 }
+
 
 // Round structure (poseidon_goldilocks.rs:927-948, the reference's `poseidon_naive`): 30 rounds of
 // [add constants, S-box, MDS]; rounds 0-3 and 26-29 apply the S-box to all 12 lanes, rounds 4-25 to lane 0 only.
@@ -137,7 +147,7 @@ __device__ __forceinline__ void pgl_mds(u64 s[12], const u64 *next_rc) {
 
 __device__ __forceinline__ void poseidon_gl_permute(u64 s[12]) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_pgl.rc[0][i]);
+    for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_pgl.rc0[i]);
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
         P2G_ROUND_SYNC();
@@ -146,7 +156,7 @@ __device__ __forceinline__ void poseidon_gl_permute(u64 s[12]) {
 #pragma unroll
             for (int i = 1; i < 12; i++) s[i] = pgl_sbox(s[i]);
         }
-        pgl_mds<true>(s, c_pgl.rc[r + 1]);  // the next round's constants ride on the fold; rc[30] = 0
+        pgl_mds(s, c_pgl.rcl[r + 1]);  // the next round's constants ride along; rcl[30] = 0
     }
 }
 

@@ -5,9 +5,14 @@
 namespace p2g {
 
 void build_poseidon_gl_tables(PoseidonGlTables *T) {
-    for (int r = 0; r < 30; r++)
-        for (int i = 0; i < 12; i++) T->rc[r][i] = P2G_GL_POSEIDON_RC[r * 12 + i] % GlHost::P;
-    for (int i = 0; i < 12; i++) T->rc[30][i] = 0;
+    for (int r = 0; r < 31; r++)
+        for (int i = 0; i < 12; i++) {
+            u64 c = r < 30 ? P2G_GL_POSEIDON_RC[r * 12 + i] % GlHost::P : 0;
+            if (r == 0) T->rc0[i] = c;
+            T->rcl[r][0][i] = (unsigned)(c & 0x3fffff);
+            T->rcl[r][1][i] = (unsigned)((c >> 22) & 0x3fffff);
+            T->rcl[r][2][i] = (unsigned)(c >> 44);
+        }
 }
 
 void build_poseidon2_bb_tables(Poseidon2BbTables *T) {

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) gl_mds_chain(const u64 *in, u64 *
 #pragma unroll 1
     for (int k = 0; k < chain; k++) {
 #pragma unroll 1
-        for (int r = 0; r < 30; r++) pgl_mds<true>(s, c_pgl.rc[r + 1]);
+        for (int r = 0; r < 30; r++) pgl_mds(s, c_pgl.rcl[r + 1]);
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) out[t * 12 + i] = gl_canon(s[i]);
