@@ -461,10 +461,15 @@ def run_ours(args, field_name):
         clk = (clocks or {}).get("sm_mhz") or 1965.0
         leaf_perms = rows_local * ((c + 7) // 8)
         measured = t_leaf * sms * 4 * clk * 1e6 / (leaf_perms / 32.0)
-        int_pipe = {"kernel": "leaf_hash_kernel", "issue_cycles_per_warp_permutation": measured,
-                    "model_cycles_per_warp_permutation": model[key]["cycles_per_warp_permutation"],
-                    "issue_slot_utilisation_vs_model": model[key]["cycles_per_warp_permutation"] / measured,
-                    "model": "profiles/r1_leaf_sponge_cost_model.json (fitted on B200: 1.42 cycles per integer warp instruction, 2.59 per IMAD.WIDE/HI; tools/sass_cost.py)"}
+        ref = model[key]
+        dyn = ref["dynamic_instructions_per_permutation"]
+        alu, fma = 2.0 * dyn["ALU pipe"], 4.0 * dyn["IMAD.WIDE/HI"] + 2.0 * dyn["other IMAD"]
+        int_pipe = {"kernel": "leaf_hash_kernel", "cycles_per_warp_permutation": measured,
+                    "microbench_cycles_per_warp_permutation": ref["measured_cycles_per_warp_permutation"],
+                    "alu_pipe_cycles": alu, "fma_pipe_cycles": fma,
+                    "busier_pipe_share_of_time": max(alu, fma) / measured,
+                    "model": "profiles/r1_leaf_sponge_cost_model.json: SASS instruction counts per permutation x 2 cycles per ALU-pipe instruction, "
+                             "4 per IMAD.WIDE/HI, 2 per other IMAD (ncu: the integer ALU pipe is half rate on B200; the pipes run concurrently)"}
     except Exception as e:  # the model file is evidence, not a dependency
         int_pipe = {"unavailable": str(e)}
     line = {
