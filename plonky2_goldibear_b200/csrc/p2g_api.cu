@@ -684,6 +684,8 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         CK(cudaEventRecord(ctx->gready[p2g_ctx::MAX_GROUPS], st));
         CK(cudaStreamWaitEvent(hs, ctx->gready[p2g_ctx::MAX_GROUPS], 0));
     }
+    // cosets transformed inside the per-group loop (see below); 5/8 of them balance a group's transforms against its upload
+    const unsigned early_cosets = pipelined ? std::max(1u, cosets_local * 5 / 8) : cosets_local;
     for (unsigned gi2 = 0; gi2 < num_groups; gi2++) {
         const unsigned col0 = gi2 * group_cols, ncol = std::min(group_cols, c - col0);
         char *g_in = (char *)d_input + (size_t)col0 * col_bytes;
@@ -710,8 +712,10 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
                 if (d->coeffs_out[j])
                     CK(cudaMemcpyAsync(d->coeffs_out[j], (char *)d_coeffs + (size_t)j * col_bytes, col_bytes, cudaMemcpyDeviceToHost, cs));
         }
-        // one coset of n rows at a time, written straight into leaf order
-        for (unsigned b = 0; b < cosets_local; b++) {
+        // one coset of n rows at a time, written straight into leaf order.  Only the first `early_cosets` of them
+        // here: that much transform work hides under the upload of the next column group; the rest follows below,
+        // coset by coset, so that finished cosets can start their way home while later ones are still computed.
+        for (unsigned b = 0; b < early_cosets; b++) {
             uint64_t shift = f_mul(f, g, f_pow(f, wN, bitrev(coset0 + b, r)));
             if ((rc = run_transform(ctx, f, repr, false, L, ncol, g_co, (char *)ctx->tmp.ptr + (size_t)col0 * col_bytes,
                                     (char *)d_leaves + (size_t)col0 * f.elem, pitch_dev, shift, (uint64_t)b * n)))
@@ -720,18 +724,26 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         CK(cudaEventRecord(ctx->tev[3 * gi2 + 2], st));
     }
     const bool leaves_early = overlap_d2h && want_leaves && !salt && cosets_local <= 62 && is_pinned(d->leaves_out);
-    if (leaves_early) {
-        // every row is final (no salt columns to add): start the D2H of the leaves, one coset per copy
-        CK(cudaEventRecord(ctx->ready[0], st));
-        CK(cudaStreamWaitEvent(cs, ctx->ready[0], 0));
-        for (unsigned b = 0; b < cosets_local; b++) {
-            char *src = (char *)d_leaves + (size_t)b * n * pitch_dev * f.elem;
-            char *dsth = (char *)d->leaves_out + (size_t)b * n * out_pitch * f.elem;
-            if (out_pitch == pitch_dev)
-                CK(cudaMemcpyAsync(dsth, src, (size_t)n * pitch_dev * f.elem, cudaMemcpyDeviceToHost, cs));
-            else
-                CK(cudaMemcpy2DAsync(dsth, out_pitch * f.elem, src, pitch_dev * f.elem, width * f.elem, n, cudaMemcpyDeviceToHost, cs));
-        }
+    auto send_coset = [&](unsigned b) -> int {
+        // every row of coset b is final (no salt columns to add): start its D2H on the copy stream
+        CK(cudaEventRecord(ctx->ready[b], st));
+        CK(cudaStreamWaitEvent(cs, ctx->ready[b], 0));
+        char *src = (char *)d_leaves + (size_t)b * n * pitch_dev * f.elem;
+        char *dsth = (char *)d->leaves_out + (size_t)b * n * out_pitch * f.elem;
+        if (out_pitch == pitch_dev)
+            CK(cudaMemcpyAsync(dsth, src, (size_t)n * pitch_dev * f.elem, cudaMemcpyDeviceToHost, cs));
+        else
+            CK(cudaMemcpy2DAsync(dsth, out_pitch * f.elem, src, pitch_dev * f.elem, width * f.elem, n, cudaMemcpyDeviceToHost, cs));
+        return 0;
+    };
+    if (leaves_early)
+        for (unsigned b = 0; b < early_cosets; b++)
+            if ((rc = send_coset(b))) return rc;
+    for (unsigned b = early_cosets; b < cosets_local; b++) {
+        uint64_t shift = f_mul(f, g, f_pow(f, wN, bitrev(coset0 + b, r)));
+        // every column is on the device by now: one launch per pass over all of them
+        if ((rc = run_transform(ctx, f, repr, false, L, c, d_coeffs, ctx->tmp.ptr, d_leaves, pitch_dev, shift, (uint64_t)b * n))) return rc;
+        if (leaves_early && (rc = send_coset(b))) return rc;
     }
     const bool leaves_sent = leaves_early;
     if (salt)
