@@ -12,12 +12,13 @@ field = p2g.GOLDILOCKS if (len(sys.argv) < 2 or sys.argv[1] == "gl") else p2g.BA
 log_n = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 c = int(sys.argv[3]) if len(sys.argv) > 3 else 135
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+repr_ = int(os.environ.get("P2G_QB_REPR", "0"))  # 1: BabyBear values are p3 Montgomery words
 ctx = p2g.Context(0)
 vals = synthetic_columns(field.order, field.dtype, c, 1 << log_n)
 cols = list(vals)
 for i in range(reps):
     t0 = time.perf_counter()
-    b = p2g.PolynomialBatch.from_values(field, cols, 3, False, 4, ctx=ctx, want_leaves=False)
+    b = p2g.PolynomialBatch.from_values(field, cols, 3, False, 4, ctx=ctx, want_leaves=False, repr=repr_)
     wall = time.perf_counter() - t0
     st = list(b.desc.stage_seconds)
     dev = sum(st)
