@@ -205,8 +205,8 @@ int32_t p2g_fri_finish(p2g_ctx *ctx, p2g_fri *fri, uint32_t rate_bits, void *fin
  * 12 (GL) / 16 (BB) state elements, input_buffer = its input_len (< 8) pending elements, all canonical, host memory.
  * Finds a witness w such that, with w observed next, the challenger's next challenge has at least min_leading_zeros
  * leading zero bits as a canonical u64 (min_leading_zeros = proof_of_work_bits + 64 - bits(order), :147).
- * The reference returns whichever candidate its thread pool hits first (find_any); this returns the smallest one of
- * the first 2^22-candidate batch that contains a hit, which is reproducible.  The caller then does
+ * The reference returns whichever candidate its thread pool hits first (find_any); this returns the smallest valid
+ * candidate (batches of 2^16..2^22 candidates are searched in increasing order), which is reproducible.  The caller then does
  * challenger.observe_element(w) and re-checks the response as the reference does (:181-186). */
 int32_t p2g_fri_pow(p2g_ctx *ctx, int32_t field, int32_t hash, const void *sponge_state, const void *input_buffer,
                     uint32_t input_len, uint32_t min_leading_zeros, uint64_t *witness_out);

@@ -692,8 +692,13 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         char *g_co = (char *)d_coeffs + (size_t)col0 * col_bytes;
         if (!dev_in) {
             cudaStream_t up = pipelined ? hs : st;
-            for (unsigned j = col0; j < col0 + ncol; j++)
-                CK(cudaMemcpyAsync((char *)h2d_base + (size_t)j * col_bytes, d->col_ptrs[j], col_bytes, cudaMemcpyHostToDevice, up));
+            for (unsigned j = col0; j < col0 + ncol;) {
+                // columns that are adjacent in host memory (a 2-D array behind the pointer table) go up in one copy
+                unsigned k = j + 1;
+                while (k < col0 + ncol && (const char *)d->col_ptrs[k] == (const char *)d->col_ptrs[k - 1] + col_bytes) k++;
+                CK(cudaMemcpyAsync((char *)h2d_base + (size_t)j * col_bytes, d->col_ptrs[j], (size_t)(k - j) * col_bytes, cudaMemcpyHostToDevice, up));
+                j = k;
+            }
             if (pipelined) {
                 CK(cudaEventRecord(ctx->gready[gi2], hs));
                 CK(cudaStreamWaitEvent(st, ctx->gready[gi2], 0));
@@ -1233,9 +1238,11 @@ int32_t p2g_fri_pow(p2g_ctx *ctx, int32_t field, int32_t hash, const void *spong
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(dev, st_host, width * f.elem, cudaMemcpyHostToDevice, st));
     const uint64_t last = (f.id == FIELD_GL ? P2G_GL_P : (uint64_t)P2G_BB_P) - 1;  // candidates run over 0..=F::neg_one() (:170)
-    const uint64_t batch = (uint64_t)1 << 22;
+    // batches in increasing candidate order, so the smallest hit of the first batch with a hit is the smallest overall;
+    // they start at 2^16 candidates (a 16-bit grind ends in the first or second one) and double up to 2^22
+    uint64_t batch = (uint64_t)1 << 16;
     const unsigned long long none = ~0ull;
-    for (uint64_t start = 0; start <= last; start += batch) {
+    for (uint64_t start = 0; start <= last; start += batch, batch = std::min<uint64_t>(batch * 2, (uint64_t)1 << 22)) {
         CK(cudaMemcpyAsync(best, &none, 8, cudaMemcpyHostToDevice, st));
         uint64_t count = std::min<uint64_t>(batch, last - start + 1);
         launch_pow_search(f.id, dev, input_len, min_leading_zeros, start, count, last, best, st, &ctx->launches);
@@ -1246,7 +1253,7 @@ int32_t p2g_fri_pow(p2g_ctx *ctx, int32_t field, int32_t hash, const void *spong
             *witness_out = got;
             return P2G_OK;
         }
-        if (start + batch < start) break;
+        if (start + batch < start) break;  // wrapped past 2^64
     }
     return ctx->fail(P2G_ERR_INVALID, "Proof of work failed. This is highly unlikely!");  // the reference's expect(), :179
 }
