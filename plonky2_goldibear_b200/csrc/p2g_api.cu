@@ -247,7 +247,7 @@ void *pool_alloc(p2g_ctx *ctx, size_t bytes) {
 void pool_free(p2g_ctx *ctx, void *p, size_t bytes) {
     if (!p) return;
     bytes = std::max<size_t>(bytes, 32);
-    if (!ctx || ctx->pool_bytes + bytes > ((size_t)48 << 30) || ctx->pool.size() >= 16) {
+    if (!ctx || ctx->pool_bytes + bytes > ((size_t)48 << 30) || ctx->pool.size() >= 96) {
         cudaFree(p);
         return;
     }
@@ -397,6 +397,22 @@ unsigned ilog2(uint64_t x) {
     unsigned l = 0;
     while (((uint64_t)1 << l) < x) l++;
     return l;
+}
+
+// device columns [first, last) -> the caller's per-column host buffers; buffers adjacent in host memory share one copy
+int copy_columns_home(p2g_ctx *ctx, void *const *dst, unsigned first, unsigned last, const void *src, size_t col_bytes,
+                      cudaStream_t stream) {
+    for (unsigned j = first; j < last;) {
+        if (!dst[j]) {
+            j++;
+            continue;
+        }
+        unsigned k = j + 1;
+        while (k < last && dst[k] && (char *)dst[k] == (char *)dst[k - 1] + col_bytes) k++;
+        CK(cudaMemcpyAsync(dst[j], (const char *)src + (size_t)j * col_bytes, (size_t)(k - j) * col_bytes, cudaMemcpyDeviceToHost, stream));
+        j = k;
+    }
+    return 0;
 }
 
 double ev_seconds(cudaEvent_t a, cudaEvent_t b) {
@@ -713,9 +729,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
             // `polynomials` of this group are final: send them home while the LDE and the hashing run
             CK(cudaEventRecord(ctx->gdone[gi2], st));
             CK(cudaStreamWaitEvent(cs, ctx->gdone[gi2], 0));
-            for (unsigned j = col0; j < col0 + ncol; j++)
-                if (d->coeffs_out[j])
-                    CK(cudaMemcpyAsync(d->coeffs_out[j], (char *)d_coeffs + (size_t)j * col_bytes, col_bytes, cudaMemcpyDeviceToHost, cs));
+            if ((rc = copy_columns_home(ctx, d->coeffs_out, col0, col0 + ncol, d_coeffs, col_bytes, cs))) return rc;
         }
         // one coset of n rows at a time, written straight into leaf order.  Only the first `early_cosets` of them
         // here: that much transform work hides under the upload of the next column group; the rest follows below,
@@ -766,9 +780,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     // ---- D2H
     if (!dev_out) {
         if (d->input_kind == P2G_INPUT_VALUES && d->coeffs_out && !coeffs_sent)
-            for (unsigned j = 0; j < c; j++)
-                if (d->coeffs_out[j])
-                    CK(cudaMemcpyAsync(d->coeffs_out[j], (char *)d_coeffs + (size_t)j * col_bytes, col_bytes, cudaMemcpyDeviceToHost, st));
+            if ((rc = copy_columns_home(ctx, d->coeffs_out, 0, c, d_coeffs, col_bytes, st))) return rc;
         if (want_leaves && !leaves_sent) {
             if (out_pitch == pitch_dev)
                 CK(cudaMemcpyAsync(d->leaves_out, d_leaves, (size_t)rows_local * pitch_dev * f.elem, cudaMemcpyDeviceToHost, st));

@@ -112,7 +112,7 @@ class PolynomialBatch:
         cap = np.empty((1 << cap_local, d), dtype=field.dtype)
         coeffs = None
         if input_kind == INPUT_VALUES and not keep_on_device:
-            coeffs = [np.empty(degree, dtype=field.dtype) for _ in cols]
+            coeffs = list(np.empty((len(cols), degree), dtype=field.dtype))  # one block: adjacent columns come back in one copy
 
         desc = _lib.CommitDesc()
         desc.field, desc.hash, desc.repr, desc.input_kind = field.field_id, field.hash_id, repr, input_kind
