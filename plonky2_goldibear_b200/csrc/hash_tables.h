@@ -2,6 +2,9 @@
 #pragma once
 #include <stdint.h>
 
+#define P2G_PGL_LIMB_ROUNDS 22  // all partial rounds, 4..25
+#define P2G_PGL_LIMB_BIAS (1u << 18)
+
 namespace p2g {
 
 struct PoseidonGlTables {
@@ -9,6 +12,12 @@ struct PoseidonGlTables {
     // constants of rounds 1..29 (and zeros for "round 30") split into the MDS layer's three limbs, bits 0-21 / 22-43 / 44-63:
     // rcl[r][k][i] = limb k of ALL_ROUND_CONSTANTS[12 r + i]; the MDS of round r-1 adds rcl[r]
     unsigned int rcl[31][3][12];
+    // limb-domain partial rounds 4..25 (poseidon_gl.cuh, pgl_partial_rounds_limbs): rclb[k] = lane 0's constant after
+    // the MDS of round 4 + k (round constants of lanes 1..11 pushed through the linear layers, bias 2^18 taken out
+    // mod p), split into limbs with the bias added back on limb 0; rc_limb_exit[i] = what lanes 1..11 still owe when
+    // they leave the loop (canonical; entry 0 unused)
+    unsigned int rclb[P2G_PGL_LIMB_ROUNDS][4];
+    unsigned long long rc_limb_exit[12];
 };
 
 struct Poseidon2BbTables {

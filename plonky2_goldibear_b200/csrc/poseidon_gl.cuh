@@ -145,9 +145,80 @@ __device__ __forceinline__ void pgl_mds(u64 s[12], const u32 (*rcl)[12]) {
 #define P2G_ROUND_SYNC() __syncthreads()
 #endif
 
+// ---- partial rounds in the limb domain ------------------------------------------------------------------------------
+// In rounds 4-25 only lane 0 meets the S-box; lanes 1..11 go from one MDS layer straight into the next.  pgl_mds pays
+// for that hand-over twice per lane and round: 2 IMAD.WIDE + an 8-instruction carry-chain fold to rebuild the u64, then
+// 5 instructions to cut it into limbs again.  Here lanes 1..11 STAY in limbs for rounds 4..25: the MDS sums (< 2^31)
+// are brought back to limb size by a carry-less pass
+//     c0 = y0 >> 22, t1 = y1 + c0, c1 = t1 >> 22, t2 = y2 + c1, top = t2 >> 20   (top < 2^9: the bits at and above 2^64)
+//     l0 = (y0 & M22) - top,  l1 = (t1 & M22) + top * 2^10,  l2 = t2 & M20        (2^64 = 2^32 - 1 mod p)
+// (10 plain 32-bit instructions, either integer pipe), leaving l0 in (-2^9, 2^22), l1 < 2^22 + 2^19, l2 < 2^20: the next
+// layer's sums stay below 264 * (2^22 + 2^19) + 2^23 < 2^31.  A slightly negative l0 could make a limb-0 sum negative,
+// so every limb-0 sum carries a bias of 2^18 (> 264 * 2^9).
+// Round constants: lanes 1..11 see only linear maps in these rounds, so their constants are pushed forward through
+// the MDS layers on the host (poseidon_tables.cpp; the reference's fast form does the same thing backwards,
+// poseidon_goldilocks.rs:304-492): with x = x' + delta, delta_0 = 0,  M S(x) + c = M S(x') + (M delta + c), so the
+// loop adds a constant to lane 0 only (rclb, with the bias taken out mod p and put back on limb 0) plus the bare bias
+// on lanes 1..11, and the accumulated delta (minus the biases) is added once on the way out (rc_limb_exit).
+// Lane 0 is rebuilt and cut every round as before (it feeds the S-box).  After round 25 the limbs are joined once
+// ( + 2^10 before the join so it never sees a negative limb, taken out again inside rc_limb_exit) for the full rounds
+// 26..29.  Same permutation bit for bit (tests: known answers, oracle parity).
+__device__ __forceinline__ void pgl_split3(u64 v, u32 &a, u32 &b, u32 &c) {
+    u32 lo = (u32)v, hi = (u32)(v >> 32);
+    a = lo & 0x3fffffu;
+    b = __funnelshift_r(lo, hi, 22) & 0x3fffffu;
+    c = hi >> 12;
+}
+__device__ __forceinline__ u64 pgl_join3(u32 y0, u32 y1, u32 y2) {
+    return pgl_fold((u64)y1 * 0x400000u + y0, (u64)y2 * 0x1000u);
+}
+
+__device__ __forceinline__ void pgl_partial_rounds_limbs(u64 s[12]) {
+    u32 l0[12], l1[12], l2[12];
+#pragma unroll
+    for (int i = 1; i < 12; i++) pgl_split3(s[i], l0[i], l1[i], l2[i]);
+    u64 s0 = s[0];
+#pragma unroll 1
+    for (int r = 0; r < P2G_PGL_LIMB_ROUNDS; r++) {
+        P2G_ROUND_SYNC();
+        s0 = pgl_sbox(s0);
+        pgl_split3(s0, l0[0], l1[0], l2[0]);
+        // constants: lane 0 gets this round's (propagated, biased) constant + the diagonal entry 8; lanes 1..11 only the
+        // bias on limb 0 (an immediate) -- their constants were pushed through the linear layers on the host
+        u32 c0[12], c1[12], c2[12];
+        c0[0] = c_pgl.rclb[r][0] + (l0[0] << 3);
+        c1[0] = c_pgl.rclb[r][1] + (l1[0] << 3);
+        c2[0] = c_pgl.rclb[r][2] + (l2[0] << 3);
+#pragma unroll
+        for (int i = 1; i < 12; i++) {
+            c0[i] = P2G_PGL_LIMB_BIAS;
+            c1[i] = 0;
+            c2[i] = 0;
+        }
+        u32 y0[12], y1[12], y2[12];
+        pgl_circ_limb(l0, y0, c0);
+        pgl_circ_limb(l1, y1, c1);
+        pgl_circ_limb(l2, y2, c2);
+        s0 = pgl_join3(y0[0], y1[0], y2[0]);
+#pragma unroll
+        for (int i = 1; i < 12; i++) {
+            u32 t1 = y1[i] + (y0[i] >> 22);
+            u32 t2 = y2[i] + (t1 >> 22);
+            u32 top = t2 >> 20;
+            l0[i] = (y0[i] & 0x3fffffu) - top;
+            l1[i] = (t1 & 0x3fffffu) + (top << 10);
+            l2[i] = t2 & 0xfffffu;
+        }
+    }
+    s[0] = s0;
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = gl_add_c(pgl_join3(l0[i] + 1024u, l1[i], l2[i]), c_pgl.rc_limb_exit[i]);
+}
+
 __device__ __forceinline__ void poseidon_gl_permute(u64 s[12]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_pgl.rc0[i]);
+#ifdef P2G_PGL_PLAIN_PARTIAL
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
         P2G_ROUND_SYNC();
@@ -158,6 +229,22 @@ __device__ __forceinline__ void poseidon_gl_permute(u64 s[12]) {
         }
         pgl_mds(s, c_pgl.rcl[r + 1]);  // the next round's constants ride along; rcl[30] = 0
     }
+#else
+    // the full rounds 0..3 and 26..29 share one body (two trips through the same loop); the 22 partial rounds run in
+    // the limb domain in between
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+        const int r_end = phase ? 30 : 4;
+#pragma unroll 1
+        for (int r = phase ? 26 : 0; r < r_end; r++) {
+            P2G_ROUND_SYNC();
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = pgl_sbox(s[i]);
+            pgl_mds(s, c_pgl.rcl[r + 1]);  // the next round's constants ride along; rcl[30] = 0
+        }
+        if (phase == 0) pgl_partial_rounds_limbs(s);
+    }
+#endif
 }
 
 #endif  // __CUDACC__
