@@ -198,9 +198,11 @@ def run_ours(args, field_name):
     es = F.elem_bytes
 
     # ---- synthetic inputs: value[col][row] = SplitMix64(seed ^ (col << 32 | row)) mod p, seed 42
-    my_cols = synthetic_columns(F.order, F.dtype, c, n)[col0:col1]
+    # (generated a few columns at a time, only this rank's: the whole matrix is 9 GB at 2^23 rows)
     host_in = ctx.pinned_empty((max(col1 - col0, 1), n), F.dtype)
-    host_in[:col1 - col0] = my_cols
+    for cb in range(col0, col1, 8):
+        ce = min(cb + 8, col1)
+        host_in[cb - col0:ce - col0] = synthetic_columns(F.order, F.dtype, ce - cb, n, col_begin=cb)
     with torch.cuda.stream(stream):
         d_vals = torch.zeros((cpr, n), dtype=tdtype, device=dev)
         d_vals[:col1 - col0].copy_(torch.from_numpy(host_in[:col1 - col0].view(np.int64 if es == 8 else np.int32)))
@@ -239,7 +241,17 @@ def run_ours(args, field_name):
     # p2g_intt_allgather) and a one-element all-reduce on the same stream is the only collective; two gather buffers
     # alternate so that a fast rank never overwrites coefficients a slow rank is still reading.  "nccl": inverse NTT into
     # a local slice, then ncclAllGather.
+    # "pipelined": the same fused kernel, but the columns travel in groups of ~64: a second context (its own stream) runs
+    # inverse NTT + peer stores + barrier for group s+1 while the main context extends group s into the leaf matrix
+    # (p2g_commit with P2G_FLAG_LEAVES_ONLY on the column range); the tree is built once every column is in
+    # (P2G_FLAG_LEAVES_READY).  Measured at 8 GPUs, 2^20 x 135: 21.1 ms (kernel stores) / 23.2 ms (copy engines) against
+    # 20.4 ms for the plain fused exchange -- the extra barriers and smaller launches cost more than the overlap hides,
+    # so "fused" stays the default.
     exchange = args.exchange if G > 1 else "none"
+    pipelined = exchange in ("pipelined", "pipelined-ce")
+    ce_copies = exchange == "pipelined-ce"  # peers receive the group through the copy engines instead of kernel stores
+    if pipelined:
+        exchange = "fused"
     gather_ptrs, peer_tables, flag = [], [], None
     if exchange == "fused":
         try:
@@ -274,7 +286,69 @@ def run_ours(args, field_name):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok) == 0:
             exchange = "nccl"
+    pipelined = pipelined and exchange == "fused"
     step_no = [0]
+
+    # ---- pipelined exchange: column groups and who owns what.  Group s = columns [s*Wg, (s+1)*Wg); inside it rank k owns
+    # the k-th slice of Wg/G columns (whole NTT tiles), so a group's columns are contiguous in the gather buffer.
+    if pipelined:
+        from plonky2_goldibear_b200.sharding import column_groups
+        group_ranges, owned = column_groups(c, G, 8 if field_name == "gl" else 16)
+        own_ranges = owned[rank]
+        own_total = sum(hi - lo for lo, hi in own_ranges)
+        p_host = ctx.pinned_empty((max(own_total, 1), n), F.dtype)
+        loc = 0
+        for lo, hi in own_ranges:
+            if hi > lo:
+                p_host[loc:loc + hi - lo] = synthetic_columns(F.order, F.dtype, hi - lo, n, col_begin=lo)
+                loc += hi - lo
+        ctx2 = p2g.Context(local_rank)  # the exchange side: its own stream and workspace
+        stream2 = torch.cuda.ExternalStream(ctx2.lib.p2g_stream(ctx2.handle), device=dev)
+        with torch.cuda.stream(stream):
+            p_vals = torch.zeros((max(own_total, 1), n), dtype=tdtype, device=dev)
+            p_vals[:own_total].copy_(torch.from_numpy(p_host[:own_total].view(np.int64 if es == 8 else np.int32)))
+        stream.synchronize()
+        ev_g = [torch.cuda.Event() for _ in group_ranges]
+        g_tbls, g_descs = [], []
+        for glo, ghi in group_ranges:
+            gd = make_desc(1, _lib.FLAG_DEVICE_INPUT | _lib.FLAG_DEVICE_OUTPUT | _lib.FLAG_LEAVES_ONLY)
+            gd.num_cols = ghi - glo
+            tbl = (ctypes.c_void_p * 1)()
+            keep.append(tbl)
+            gd.col_ptrs = ctypes.cast(tbl, ctypes.POINTER(ctypes.c_void_p))
+            gd.leaves_out, gd.leaf_pitch = d_leaves.data_ptr() + glo * es, c
+            g_tbls.append(tbl)
+            g_descs.append(gd)
+        tree_desc = make_desc(1, _lib.FLAG_DEVICE_INPUT | _lib.FLAG_DEVICE_OUTPUT | _lib.FLAG_LEAVES_READY)
+        tree_desc.leaves_out, tree_desc.leaf_pitch = d_leaves.data_ptr(), c
+        tree_desc.digests_out, tree_desc.cap_out = d_digests.data_ptr(), d_cap.data_ptr()
+
+    def pipelined_step():
+        k = step_no[0] & 1
+        step_no[0] += 1
+        loc = 0
+        for s_, (lo, hi) in enumerate(own_ranges):
+            if hi > lo and not ce_copies:
+                ctx2.check(ctx2.lib.p2g_intt_allgather(ctx2.handle, F.field_id, 0, L, hi - lo, lo,
+                                                       p_vals.data_ptr() + loc * n * es, peer_tables[k], G))
+                loc += hi - lo
+            elif hi > lo:
+                ctx2.check(ctx2.lib.p2g_intt_allgather(ctx2.handle, F.field_id, 0, L, hi - lo, lo,
+                                                       p_vals.data_ptr() + loc * n * es, peer_tables[k], 1))
+                off, nb = lo * n * es, (hi - lo) * n * es
+                for pk in range(1, G):
+                    ctx2.check(ctx2.lib.p2g_memcpy_async(ctx2.handle, peer_tables[k][pk] + off, gather_ptrs[k] + off, nb, 2))
+                loc += hi - lo
+            with torch.cuda.stream(stream2):
+                dist.all_reduce(flag)  # every rank's stores of this group have landed
+                ev_g[s_].record(stream2)
+        for s_, (glo, ghi) in enumerate(group_ranges):
+            stream.wait_event(ev_g[s_])
+            g_tbls[s_][0] = gather_ptrs[k] + glo * n * es
+            ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(g_descs[s_])))
+            kernel_s[:] += np.array(list(g_descs[s_].kernel_seconds))
+        ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(tree_desc)))
+        kernel_s[:] += np.array(list(tree_desc.kernel_seconds))
 
     def exchange_coeffs(d2h_slice=None):
         """inverse NTT of this rank's columns + all-gather; returns the device pointer holding all coefficients"""
@@ -308,6 +382,8 @@ def run_ours(args, field_name):
     keep.append(coeff_tbl)
 
     def device_step():
+        if pipelined:
+            return pipelined_step()
         if G > 1:
             coeff_tbl[0] = exchange_coeffs()
             dev_desc.col_ptrs = ctypes.cast(coeff_tbl, ctypes.POINTER(ctypes.c_void_p))
@@ -338,13 +414,14 @@ def run_ours(args, field_name):
     for _ in range(args.warmup):
         device_step()
     kernel_s[:] = 0
-    launches0 = ctx.kernel_launches()
+    launches0 = ctx.kernel_launches() + (ctx2.kernel_launches() if pipelined else 0)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     dev_total, _ = timed(device_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    launches = ctx.kernel_launches() - launches0
+    launches = ctx.kernel_launches() + (ctx2.kernel_launches() if pipelined else 0) - launches0
+    args.exchange = ("pipelined-ce" if ce_copies else "pipelined") if pipelined else (exchange if G > 1 else None)  # what actually ran
     t_step = dev_total / args.steps
     ksec = kernel_s / args.steps
     value = (c << L) / t_step
@@ -581,9 +658,10 @@ def main():
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+    ap.add_argument("--exchange", default="fused", choices=["fused", "pipelined", "pipelined-ce", "nccl"],
                     help="multi-GPU coefficient exchange: inverse NTT with the all-gather fused into its epilogue over "
-                         "peer memory (default), or a separate ncclAllGather")
+                         "peer memory (default); the same in column groups overlapped with the LDE (pipelined: kernel "
+                         "stores, pipelined-ce: copy engines; both measured slower, DESIGN.md section 5); or a separate ncclAllGather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fri", action="store_true", help="skip the secondary FRI commit-phase measurement")
     ap.add_argument("--cpu-sample-log-n", type=int, default=16)

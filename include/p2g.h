@@ -78,6 +78,14 @@ void p2g_host_free(p2g_ctx *ctx, void *ptr);
                                       are then fetched on demand (p2g_batch_*): the device-resident form of
                                       get_lde_values / MerkleTree::get / MerkleTree::prove */
 
+/* A commit split over column ranges (multi-GPU pipelines: the LDE of the columns that have arrived runs while the
+ * exchange of the next ones is still in flight).  Both need P2G_FLAG_DEVICE_OUTPUT and a device leaves_out. */
+#define P2G_FLAG_LEAVES_ONLY 16u  /* stop after "transpose LDEs": the num_cols columns given are extended into columns
+                                     [0, num_cols) of the rows at leaves_out (leaf_pitch >= num_cols; point leaves_out at
+                                     the first column of the range inside a wider leaf matrix); nothing is hashed */
+#define P2G_FLAG_LEAVES_READY 32u /* "build Merkle tree" only: leaves_out already holds this shard's rows, num_cols
+                                     (+ salt) wide at leaf_pitch; col_ptrs is ignored */
+
 typedef struct p2g_batch p2g_batch;
 
 /* One call = one PolynomialBatch::from_values (input_kind VALUES) or from_coeffs (COEFFS). */

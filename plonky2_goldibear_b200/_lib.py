@@ -12,6 +12,8 @@ FLAG_DEVICE_INPUT = 1
 FLAG_DEVICE_OUTPUT = 2
 FLAG_NO_LEAVES_OUT = 4
 FLAG_KEEP_ON_DEVICE = 8
+FLAG_LEAVES_ONLY = 16
+FLAG_LEAVES_READY = 32
 
 ERR_NAMES = {0: "OK", -1: "INVALID", -2: "NO_DEVICE", -3: "CUDA", -4: "OOM", -5: "UNSUPPORTED"}
 

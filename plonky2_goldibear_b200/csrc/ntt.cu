@@ -198,6 +198,34 @@ __device__ __forceinline__ u32 natural_to_chunk(u32 d, u32 lp1, u32 lp2) {
     return (f1 << lp2) + f2;
 }
 
+// epilogue of a strided pass: tile element idx = (pp << lw) + w holds frequency f = bitrev(pp) of run element w; it is
+// multiplied by the inter-pass factor and stored at chunk + (f << lmo) + jt*W + w.  Factors are read a batch ahead of
+// the multiplications.  GUARD = false when the tile is a whole number of batches (every large tile).
+template <class F, bool GUARD>
+__device__ __forceinline__ void strided_store(const typename F::E *x, typename F::E *dst, const typename F::E *tw, u32 total,
+                                              u32 lp, u32 lw, u32 lmo, u32 jt) {
+    typedef typename F::E E;
+    constexpr u32 B = 8;
+    const u32 W = 1u << lw;
+    for (u32 idx0 = threadIdx.x; idx0 < total; idx0 += blockDim.x * B) {
+        E t[B];
+        u32 pos[B];
+#pragma unroll
+        for (u32 k = 0; k < B; k++) {
+            u32 idx = idx0 + k * blockDim.x;
+            u32 w = idx & (W - 1), pp = idx >> lw;
+            u32 f = __brev(pp) >> (32 - lp);
+            pos[k] = (f << lmo) + (jt << lw) + w;
+            if (!GUARD || idx < total) t[k] = tw[pos[k]];
+        }
+#pragma unroll
+        for (u32 k = 0; k < B; k++) {
+            u32 idx = idx0 + k * blockDim.x;
+            if (!GUARD || idx < total) dst[pos[k]] = F::mul(x[idx], t[k]);  // internal representation
+        }
+    }
+}
+
 template <class F>
 __global__ void __launch_bounds__(256, 3) ntt_strided_kernel(NttPass p) {
     typedef typename F::E E;
@@ -220,11 +248,19 @@ __global__ void __launch_bounds__(256, 3) ntt_strided_kernel(NttPass p) {
     // stage the raw tile: row i is a run of W consecutive elements at src[(i << lmo) + jt*W]
     const u32 run_bytes = (u32)sizeof(E) << lw;
     if (p.async_ok && run_bytes >= 16) {
-        const u32 per_row = run_bytes >> 4;  // 16-byte pieces per row
-        for (u32 c16 = threadIdx.x; c16 < np * per_row; c16 += blockDim.x) {
-            u32 i = c16 / per_row, part = c16 - i * per_row;
-            cp_async16((char *)x + (size_t)i * run_bytes + part * 16,
-                       (const char *)(src + ((size_t)i << lmo) + (jt << lw)) + part * 16);
+        // 16-byte pieces; a thread keeps its piece of the run and walks down the rows (block size is a multiple of the
+        // pieces per row), so the loop is a copy and two pointer increments
+        const u32 lpr = 31 - __clz(run_bytes >> 4);  // log2(pieces per row)
+        const u32 part = threadIdx.x & ((1u << lpr) - 1), rows_step = blockDim.x >> lpr;
+        const char *g = (const char *)(src + (jt << lw)) + part * 16 + (((size_t)(threadIdx.x >> lpr) << lmo) * sizeof(E));
+        char *sm = (char *)x + (size_t)(threadIdx.x >> lpr) * run_bytes + part * 16;
+        const size_t g_step = ((size_t)rows_step << lmo) * sizeof(E);
+        const u32 s_step = rows_step * run_bytes;
+#pragma unroll 4
+        for (u32 i = threadIdx.x >> lpr; i < np; i += rows_step) {
+            cp_async16(sm, g);
+            g += g_step;
+            sm += s_step;
         }
     } else {
         for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -239,24 +275,10 @@ __global__ void __launch_bounds__(256, 3) ntt_strided_kernel(NttPass p) {
     LoadFix<F> fix = {(const E *)p.scale_table, p.in_user_repr != 0};
     dif_stages<F, true>(x, roots_s, lp, lw, W, 1, fix);
     // store with the inter-pass factor; the factor table is indexed like the store, read a batch ahead
-    constexpr u32 B = 8;
-    for (u32 idx0 = threadIdx.x; idx0 < total; idx0 += blockDim.x * B) {
-        E t[B];
-        u32 pos[B];
-#pragma unroll
-        for (u32 k = 0; k < B; k++) {
-            u32 idx = idx0 + k * blockDim.x;
-            u32 w = idx & (W - 1), pp = idx >> lw;
-            u32 f = __brev(pp) >> (32 - lp);
-            pos[k] = (f << lmo) + (jt << lw) + w;
-            if (idx < total) t[k] = tw[pos[k]];
-        }
-#pragma unroll
-        for (u32 k = 0; k < B; k++) {
-            u32 idx = idx0 + k * blockDim.x;
-            if (idx < total) dst[pos[k]] = F::mul(x[idx], t[k]);  // internal representation
-        }
-    }
+    if (total % (blockDim.x * 8) == 0)
+        strided_store<F, false>(x, dst, tw, total, lp, lw, lmo, jt);
+    else
+        strided_store<F, true>(x, dst, tw, total, lp, lw, lmo, jt);
 }
 
 template <class F>
@@ -280,10 +302,16 @@ __global__ void __launch_bounds__(256, 3) ntt_final_natural_kernel(NttPass p) {
     const u32 chunk_bytes = (u32)sizeof(E) << lp;
     if (p.async_ok && chunk_bytes >= 16) {
         const u32 per_chunk = chunk_bytes >> 4;
-        for (u32 c16 = threadIdx.x; c16 < (per_chunk << lw); c16 += blockDim.x) {
-            u32 w = c16 / per_chunk, part = c16 - w * per_chunk;
-            u32 q = natural_to_chunk(d0 + w, p.lp1, p.lp2);
-            cp_async16((char *)(x + (size_t)w * S) + part * 16, (const char *)(src + ((size_t)q << lp)) + part * 16);
+        for (u32 w = 0; w < W; w++) {
+            const u32 q = natural_to_chunk(d0 + w, p.lp1, p.lp2);
+            const char *g = (const char *)(src + ((size_t)q << lp)) + threadIdx.x * 16;
+            char *sm = (char *)(x + (size_t)w * S) + threadIdx.x * 16;
+#pragma unroll 4
+            for (u32 part = threadIdx.x; part < per_chunk; part += blockDim.x) {
+                cp_async16(sm, g);
+                g += blockDim.x * 16;
+                sm += blockDim.x * 16;
+            }
         }
     } else {
         for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -332,9 +360,15 @@ __global__ void __launch_bounds__(256, 3) ntt_final_leaves_kernel(NttPass p) {
     const u32 chunk_bytes = (u32)sizeof(E) << lp;
     if (p.async_ok && chunk_bytes >= 16) {
         const u32 per_chunk = chunk_bytes >> 4;
-        for (u32 c16 = threadIdx.x; c16 < per_chunk * ncols; c16 += blockDim.x) {
-            u32 w = c16 / per_chunk, part = c16 - w * per_chunk;
-            cp_async16((char *)(x + (size_t)w * S) + part * 16, (const char *)(src + (size_t)w * p.src_col_stride) + part * 16);
+        for (u32 w = 0; w < ncols; w++) {
+            const char *g = (const char *)(src + (size_t)w * p.src_col_stride) + threadIdx.x * 16;
+            char *sm = (char *)(x + (size_t)w * S) + threadIdx.x * 16;
+#pragma unroll 4
+            for (u32 part = threadIdx.x; part < per_chunk; part += blockDim.x) {
+                cp_async16(sm, g);
+                g += blockDim.x * 16;
+                sm += blockDim.x * 16;
+            }
         }
     } else {
         for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -357,12 +391,29 @@ __global__ void __launch_bounds__(256, 3) ntt_final_leaves_kernel(NttPass p) {
     const u32 dq = chunk_to_natural(q, p.lp1, p.lp2);
     const u32 rq = lc ? (__brev(dq) >> (32 - lc)) : 0;
     E *rows = (E *)p.dst + (p.row_base + ((size_t)rq << lp)) * p.dst_col_stride + col0;
-    for (u32 idx = threadIdx.x; idx < (np << F::W_LOG); idx += blockDim.x) {
-        u32 w = idx & (W - 1), pp = idx >> F::W_LOG;
+    {
+        // a thread keeps its column and walks down the rows (block size is a multiple of W): one shared load, the
+        // representation change and one store per element, pointers advanced by constants
+        const u32 w = threadIdx.x & (W - 1), pp0 = threadIdx.x >> F::W_LOG, step = blockDim.x >> F::W_LOG;
         if (w < ncols) {
-            E v = x[w * S + pp];
-            if (p.out_user_repr) v = F::store_user(v);
-            rows[(size_t)pp * p.dst_col_stride + w] = v;
+            const E *sm = x + w * S + pp0;
+            E *out = rows + (size_t)pp0 * p.dst_col_stride + w;
+            const size_t out_step = (size_t)step * p.dst_col_stride;
+            if (p.out_user_repr) {
+#pragma unroll 4
+                for (u32 pp = pp0; pp < np; pp += step) {
+                    *out = F::store_user(*sm);
+                    sm += step;
+                    out += out_step;
+                }
+            } else {
+#pragma unroll 4
+                for (u32 pp = pp0; pp < np; pp += step) {
+                    *out = *sm;
+                    sm += step;
+                    out += out_step;
+                }
+            }
         }
     }
 }

@@ -554,7 +554,11 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     if (LN > 30 || L > 3 * MAX_TILE_LOG) return ctx->fail(P2G_ERR_UNSUPPORTED, "LDE size 2^%u too large for this build", LN);
     if (d->cap_height > LN) return ctx->fail(P2G_ERR_INVALID, "cap_height=%u should be at most log2(leaves.len())=%u", d->cap_height, LN);
     if (d->num_salt_cols && !d->salt_ptrs) return ctx->fail(P2G_ERR_INVALID, "salt columns requested without salt_ptrs");
-    if (!d->col_ptrs) return ctx->fail(P2G_ERR_INVALID, "col_ptrs is NULL");
+    const bool leaves_only = d->flags & P2G_FLAG_LEAVES_ONLY, leaves_ready = d->flags & P2G_FLAG_LEAVES_READY;
+    if (leaves_only && leaves_ready) return ctx->fail(P2G_ERR_INVALID, "LEAVES_ONLY and LEAVES_READY are exclusive");
+    if ((leaves_only || leaves_ready) && (!(d->flags & P2G_FLAG_DEVICE_OUTPUT) || (d->flags & P2G_FLAG_KEEP_ON_DEVICE) || !d->leaves_out))
+        return ctx->fail(P2G_ERR_INVALID, "LEAVES_ONLY / LEAVES_READY need P2G_FLAG_DEVICE_OUTPUT and a device leaves_out");
+    if (!d->col_ptrs && !leaves_ready) return ctx->fail(P2G_ERR_INVALID, "col_ptrs is NULL");
     unsigned G = d->shard_count ? d->shard_count : 1, gi = d->shard_count ? d->shard_index : 0;
     if (G & (G - 1)) return ctx->fail(P2G_ERR_INVALID, "shard_count must be a power of two");
     if (gi >= G) return ctx->fail(P2G_ERR_INVALID, "shard_index out of range");
@@ -568,25 +572,30 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     const unsigned tree_log = LN - lg, cap_local = d->cap_height >= lg ? d->cap_height - lg : 0;
     const uint64_t num_cap_local = (uint64_t)1 << cap_local;
     const uint64_t num_digests_local = 2 * (rows_local - num_cap_local);
-    const uint64_t pitch_dev = width;
     const bool keep = d->flags & P2G_FLAG_KEEP_ON_DEVICE;
+    // device-resident leaves are written (and hashed) in place at the caller's pitch
+    const uint64_t pitch_dev = ((d->flags & P2G_FLAG_DEVICE_OUTPUT) && !keep && d->leaves_out && d->leaf_pitch &&
+                                !(d->flags & P2G_FLAG_NO_LEAVES_OUT)) ? d->leaf_pitch : width;
     if (keep && !d->batch_out) return ctx->fail(P2G_ERR_INVALID, "P2G_FLAG_KEEP_ON_DEVICE needs batch_out");
     if (keep && (d->flags & P2G_FLAG_DEVICE_OUTPUT)) return ctx->fail(P2G_ERR_INVALID, "KEEP_ON_DEVICE and DEVICE_OUTPUT are exclusive");
     const bool dev_in = d->flags & P2G_FLAG_DEVICE_INPUT, dev_out = (d->flags & P2G_FLAG_DEVICE_OUTPUT) || keep;
     const bool want_leaves = keep || (!(d->flags & P2G_FLAG_NO_LEAVES_OUT) && d->leaves_out);
     const uint64_t out_pitch = d->leaf_pitch ? d->leaf_pitch : width;
     if (out_pitch < width) return ctx->fail(P2G_ERR_INVALID, "leaf_pitch smaller than the leaf length");
+    if ((leaves_only || leaves_ready) && !want_leaves) return ctx->fail(P2G_ERR_INVALID, "LEAVES_ONLY / LEAVES_READY with NO_LEAVES_OUT");
 
     const size_t col_bytes = n * f.elem;
     cudaStream_t st = ctx->stream;
     // ---- workspace
-    if (!dev_in || d->input_kind == P2G_INPUT_VALUES) {
-        if ((rc = ensure(ctx, ctx->in, (size_t)c * col_bytes))) return rc;
+    if (!leaves_ready) {
+        if (!dev_in || d->input_kind == P2G_INPUT_VALUES) {
+            if ((rc = ensure(ctx, ctx->in, (size_t)c * col_bytes))) return rc;
+        }
+        if (d->input_kind == P2G_INPUT_VALUES)
+            if ((rc = ensure(ctx, ctx->coeffs, (size_t)c * col_bytes))) return rc;
+        if (L > MAX_TILE_LOG)
+            if ((rc = ensure(ctx, ctx->tmp, (size_t)c * col_bytes))) return rc;
     }
-    if (d->input_kind == P2G_INPUT_VALUES)
-        if ((rc = ensure(ctx, ctx->coeffs, (size_t)c * col_bytes))) return rc;
-    if (L > MAX_TILE_LOG)
-        if ((rc = ensure(ctx, ctx->tmp, (size_t)c * col_bytes))) return rc;
     // a kept batch owns fresh device buffers instead of borrowing the context's workspace
     p2g_batch *batch = nullptr;
     struct BatchGuard {
@@ -635,7 +644,9 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         d_leaves = ctx->leaves.ptr;
     }
     void *d_digests = nullptr, *d_cap = nullptr;
-    if (keep) {
+    if (leaves_only) {
+        // no tree in this call
+    } else if (keep) {
         d_digests = batch->digests;
     } else if (dev_out && d->digests_out) {
         d_digests = d->digests_out;
@@ -643,13 +654,32 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         if ((rc = ensure(ctx, ctx->digests, std::max<size_t>(32, num_digests_local * 32)))) return rc;
         d_digests = ctx->digests.ptr;
     }
-    if (keep) {
+    if (leaves_only) {
+    } else if (keep) {
         d_cap = batch->cap;
     } else if (dev_out && d->cap_out) {
         d_cap = d->cap_out;
     } else {
         if ((rc = ensure(ctx, ctx->cap, num_cap_local * 32))) return rc;
         d_cap = ctx->cap.ptr;
+    }
+
+    if (leaves_ready) {
+        // the caller filled this shard's rows (several LEAVES_ONLY calls over column ranges): "build Merkle tree" only
+        CK(cudaEventRecord(ctx->ev[3], st));
+        TreeShape tree = {tree_log, cap_local, d_digests, d_cap};
+        launch_leaf_hash(f.id, repr, d_leaves, pitch_dev, width, 0, rows_local, tree, st, &ctx->launches);
+        CK(cudaEventRecord(ctx->ev[6], st));
+        launch_tree_levels(f.id, repr, tree, st, &ctx->launches);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[4], st));
+        CK(cudaStreamSynchronize(st));
+        for (int k = 0; k < 4; k++) d->stage_seconds[k] = d->kernel_seconds[k] = 0.0;
+        d->h2d_seconds = d->d2h_seconds = 0.0;
+        d->stage_seconds[3] = ev_seconds(ctx->ev[3], ctx->ev[4]);
+        d->kernel_seconds[2] = ev_seconds(ctx->ev[3], ctx->ev[6]);
+        d->kernel_seconds[3] = ev_seconds(ctx->ev[6], ctx->ev[4]);
+        return P2G_OK;
     }
 
     // ---- H2D, "IFFT", "FFT + blinding" + "transpose LDEs"
@@ -768,6 +798,25 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     if (salt)
         launch_salt_scatter(f.id, ctx->salts.ptr, salt, LN, row0, rows_local, d_leaves, pitch_dev, c, st, &ctx->launches);
     CK(cudaEventRecord(ctx->ev[3], st));
+    if (leaves_only) {
+        // the rows' column range [0, width) at leaves_out is final; the tree is built by a later LEAVES_READY call
+        CK(cudaStreamSynchronize(st));
+        CK(cudaStreamSynchronize(cs));
+        CK(cudaStreamSynchronize(hs));
+        d->h2d_seconds = ev_seconds(ctx->ev[0], ctx->ev[1]);
+        d->d2h_seconds = 0.0;
+        d->stage_seconds[0] = d->stage_seconds[1] = 0.0;
+        for (unsigned gi2 = 0; gi2 < num_groups; gi2++) {
+            d->stage_seconds[0] += ev_seconds(ctx->tev[3 * gi2], ctx->tev[3 * gi2 + 1]);
+            d->stage_seconds[1] += ev_seconds(ctx->tev[3 * gi2 + 1], ctx->tev[3 * gi2 + 2]);
+        }
+        d->stage_seconds[1] += ev_seconds(ctx->tev[3 * (num_groups - 1) + 2], ctx->ev[3]);
+        d->stage_seconds[2] = d->stage_seconds[3] = 0.0;
+        d->kernel_seconds[0] = d->stage_seconds[0];
+        d->kernel_seconds[1] = d->stage_seconds[1];
+        d->kernel_seconds[2] = d->kernel_seconds[3] = 0.0;
+        return P2G_OK;
+    }
 
     // ---- "build Merkle tree"
     TreeShape tree = {tree_log, cap_local, d_digests, d_cap};

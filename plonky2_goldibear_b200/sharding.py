@@ -54,3 +54,19 @@ def plan(rank: int, world: int, num_cols: int, log_n: int, rate_bits: int, cap_h
     return ShardPlan(rank, world, cpr, min(rank * cpr, num_cols), min((rank + 1) * cpr, num_cols),
                      rank * cosets, (rank + 1) * cosets, rank * rows, (rank + 1) * rows, local_h,
                      dig[0], dig[1], cap[0], cap[1], whole)
+
+
+def column_groups(num_cols: int, world: int, tile_cols: int):
+    """Column groups of the pipelined exchange (bench.py --exchange pipelined): the coefficient columns cross NVLink in
+    groups of about half the batch so that the LDE of group s overlaps the inverse NTT + peer stores of group s+1.
+    Group s = columns [s*Wg, (s+1)*Wg) with Wg a multiple of world*tile_cols (whole NTT column tiles per rank); inside a
+    group rank k owns the k-th slice of Wg/world columns.  Returns (groups, owned): groups[s] = (lo, hi),
+    owned[k][s] = (lo, hi) of rank k in group s (possibly empty in a ragged last group)."""
+    if world <= 0 or world & (world - 1):
+        raise ValueError("world size must be a power of two")
+    unit = world * tile_cols
+    wg = max(unit, (num_cols // 2) // unit * unit)
+    t = wg // world
+    groups = [(lo, min(lo + wg, num_cols)) for lo in range(0, num_cols, wg)]
+    owned = [[(min(glo + k * t, ghi), min(glo + (k + 1) * t, ghi)) for glo, ghi in groups] for k in range(world)]
+    return groups, owned

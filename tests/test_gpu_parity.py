@@ -435,3 +435,67 @@ def test_fused_intt_allgather_emulated_on_one_gpu(ctx, oracle):
         for b in bufs:
             got = b.cpu().numpy().view(F.dtype)[:c]
             assert (got == exp).all()
+
+
+@pytest.mark.parametrize("field,log_n,c,r,h,g,groups", [(0, 11, 19, 3, 4, 1, (8, 8, 3)), (0, 10, 21, 3, 4, 4, (16, 5)),
+                                                        (1, 11, 40, 3, 4, 2, (32, 8)), (0, 12, 9, 2, 1, 1, (9,))])
+def test_commit_split_over_column_ranges(ctx, oracle, field, log_n, c, r, h, g, groups):
+    """P2G_FLAG_LEAVES_ONLY / LEAVES_READY: the LDE of column ranges written straight into one device-resident leaf
+    matrix (as the pipelined multi-GPU exchange does, group by group), then the tree over the finished rows -- leaves,
+    digests and cap equal the one-shot commit's (and the oracle's) for the shard."""
+    import ctypes
+    import torch
+    from plonky2_goldibear_b200 import _lib
+    F = fields()[field]
+    n, N = 1 << log_n, 1 << (log_n + r)
+    vals = synthetic_columns(F.order, F.dtype, c, n, seed=33)
+    ref = oracle.commit(field, vals, oracle.VALUES, r, h)
+    coeffs = np.ascontiguousarray(ref["coeffs"])
+    tdt, ndt = (torch.int64, np.int64) if field == 0 else (torch.int32, np.int32)
+    d_el = F.num_hash_out_elts
+    lg = g.bit_length() - 1
+    rows_local, cap_local = N // g, max(h - lg, 0)
+    d_coeffs = torch.from_numpy(coeffs.view(ndt)).cuda()
+    keep = []
+    for shard in range(g):
+        d_leaves = torch.zeros((rows_local, c), dtype=tdt, device="cuda")
+        d_dig = torch.zeros((max(2 * (rows_local - (1 << cap_local)), 1), d_el), dtype=tdt, device="cuda")
+        d_cap = torch.zeros((1 << cap_local, d_el), dtype=tdt, device="cuda")
+        torch.cuda.synchronize()
+
+        def desc_for(num_cols, flags):
+            d = _lib.CommitDesc()
+            d.field, d.hash, d.repr, d.input_kind = F.field_id, F.hash_id, 0, 1
+            d.log_n, d.num_cols, d.rate_bits, d.cap_height = log_n, num_cols, r, h
+            d.flags = _lib.FLAG_DEVICE_INPUT | _lib.FLAG_DEVICE_OUTPUT | flags
+            d.shard_index, d.shard_count = (shard, g) if g > 1 else (0, 0)
+            d.leaf_pitch = c
+            return d
+        col = 0
+        for gc in groups:
+            d = desc_for(gc, _lib.FLAG_LEAVES_ONLY)
+            arr = (ctypes.c_void_p * 1)(d_coeffs.data_ptr() + col * n * F.elem_bytes)
+            keep.append(arr)
+            d.col_ptrs = ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
+            d.leaves_out = d_leaves.data_ptr() + col * F.elem_bytes
+            ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(d)))
+            col += gc
+        assert col == c
+        d = desc_for(c, _lib.FLAG_LEAVES_READY)
+        d.leaves_out, d.digests_out, d.cap_out = d_leaves.data_ptr(), d_dig.data_ptr(), d_cap.data_ptr()
+        ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(d)))
+        torch.cuda.synchronize()
+        r0 = shard * rows_local
+        assert (d_leaves.cpu().numpy().view(F.dtype) == ref["leaves"][r0:r0 + rows_local]).all()
+        if g == 1:
+            assert (d_cap.cpu().numpy().view(F.dtype) == ref["cap"]).all()
+            assert (d_dig.cpu().numpy().view(F.dtype)[:len(ref["digests"])] == ref["digests"]).all()
+        else:
+            one = ctx_commit_shard(ctx, F, vals, r, h, shard, g)
+            assert (d_cap.cpu().numpy().view(F.dtype) == one.merkle_tree.cap.hashes).all()
+            assert (d_dig.cpu().numpy().view(F.dtype)[:len(one.merkle_tree.digests)] == one.merkle_tree.digests).all()
+
+
+def ctx_commit_shard(ctx, F, vals, r, h, shard, g):
+    import plonky2_goldibear_b200 as p2g
+    return p2g.PolynomialBatch.from_values(F, list(vals), r, False, h, ctx=ctx, shard_index=shard, shard_count=g)

@@ -86,3 +86,23 @@ def test_plan_rejects_bad_worlds():
     assert (sp.col_begin, sp.col_end, sp.cols_per_rank) == (119, 135, 17)
     assert (sp.coset_begin, sp.coset_end) == (7, 8) and sp.local_cap_height == 1
     assert sp.row_end == 1 << 23 and sp.cap_end == 16
+
+
+def test_pipelined_exchange_column_groups_cover_every_column_once():
+    """bench.py --exchange pipelined: groups are contiguous, ranks own disjoint whole-tile slices, nothing is lost."""
+    from plonky2_goldibear_b200.sharding import column_groups
+    for c, world, tile in ((135, 8, 8), (135, 4, 8), (135, 2, 8), (256, 8, 16), (256, 2, 16), (5, 8, 8), (64, 8, 8), (1, 1, 8)):
+        groups, owned = column_groups(c, world, tile)
+        assert groups[0][0] == 0 and groups[-1][1] == c
+        assert all(a[1] == b[0] for a, b in zip(groups, groups[1:]))
+        seen = []
+        for k in range(world):
+            assert len(owned[k]) == len(groups)
+            for (lo, hi), (glo, ghi) in zip(owned[k], groups):
+                assert glo <= lo <= hi <= ghi
+                if hi > lo and hi != ghi:
+                    assert (hi - lo) % tile == 0  # whole NTT column tiles except at the ragged end
+                seen += list(range(lo, hi))
+        assert sorted(seen) == list(range(c))
+    groups, _ = column_groups(135, 8, 8)
+    assert groups == [(0, 64), (64, 128), (128, 135)]

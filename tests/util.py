@@ -13,10 +13,10 @@ def splitmix64(x: np.ndarray) -> np.ndarray:
     return z ^ (z >> np.uint64(31))
 
 
-def synthetic_columns(order: int, dtype, num_cols: int, n: int, seed: int = 42) -> np.ndarray:
-    """value[col][row] = SplitMix64(seed ^ (col << 32 | row)) mod p"""
+def synthetic_columns(order: int, dtype, num_cols: int, n: int, seed: int = 42, col_begin: int = 0) -> np.ndarray:
+    """value[col][row] = SplitMix64(seed ^ (col << 32 | row)) mod p, for columns col_begin .. col_begin + num_cols - 1"""
     with np.errstate(over="ignore"):
-        col = np.arange(num_cols, dtype=np.uint64)[:, None] << np.uint64(32)
+        col = np.arange(col_begin, col_begin + num_cols, dtype=np.uint64)[:, None] << np.uint64(32)
         row = np.arange(n, dtype=np.uint64)[None, :]
         v = splitmix64(np.uint64(seed) ^ (col | row))
     return (v % np.uint64(order)).astype(dtype)
