@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(256, 3) ntt_strided_kernel(NttPass p) {
     E *x = reinterpret_cast<E *>(smem_raw);
     const u32 lp = p.log_np, np = 1u << lp;
     const u32 lmo = p.log_min - lp;                           // log2(m_out)
-    const u32 lw = lmo < (u32)F::W_LOG ? lmo : (u32)F::W_LOG;  // tile width (runs of 2^lw elements)
+    const u32 wl = tile_width_log(F::W_LOG, lp);
+    const u32 lw = lmo < wl ? lmo : wl;  // tile width (runs of 2^lw elements)
     const u32 W = 1u << lw;
     E *roots_s = x + ((size_t)np << lw);
     const u32 tiles_per_chunk = 1u << (lmo - lw);
@@ -288,7 +289,8 @@ __global__ void __launch_bounds__(256, 3) ntt_final_natural_kernel(NttPass p) {
     E *x = reinterpret_cast<E *>(smem_raw);
     const u32 lp = p.log_np, np = 1u << lp;
     const u32 lc = p.log_n - lp;                              // log2(chunks per column)
-    const u32 lw = lc < (u32)F::W_LOG ? lc : (u32)F::W_LOG;  // chunks per tile
+    const u32 wl = tile_width_log(F::W_LOG, lp);
+    const u32 lw = lc < wl ? lc : wl;  // chunks per tile
     const u32 W = 1u << lw;
     const u32 S = np + F::PAD;
     E *roots_s = x + (size_t)S * W;
@@ -347,13 +349,14 @@ __global__ void __launch_bounds__(256, 3) ntt_final_leaves_kernel(NttPass p) {
     E *x = reinterpret_cast<E *>(smem_raw);
     const u32 lp = p.log_np, np = 1u << lp;
     const u32 lc = p.log_n - lp;
-    const u32 W = 1u << F::W_LOG;  // columns per tile
+    const u32 wl = tile_width_log(F::W_LOG, lp);
+    const u32 W = 1u << wl;  // columns per tile
     const u32 S = np + F::PAD;
     E *roots_s = x + (size_t)S * W;
-    const u32 col_groups = (p.num_cols + W - 1) >> F::W_LOG;
+    const u32 col_groups = (p.num_cols + W - 1) >> wl;
     const u32 q = blockIdx.x / col_groups;
     const u32 cg = blockIdx.x - q * col_groups;
-    const u32 col0 = cg << F::W_LOG;
+    const u32 col0 = cg << wl;
     const u32 ncols = min(W, p.num_cols - col0);
     const E *src = (const E *)p.src + (size_t)col0 * p.src_col_stride + ((size_t)q << lp);
     const u32 total = np * ncols;
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(256, 3) ntt_final_leaves_kernel(NttPass p) {
         }
     }
     // unused column slots of a ragged last tile must still hold defined values for the butterflies
-    for (u32 idx = total + threadIdx.x; idx < (np << F::W_LOG); idx += blockDim.x) {
+    for (u32 idx = total + threadIdx.x; idx < (np << wl); idx += blockDim.x) {
         u32 i = idx & (np - 1), w = idx >> lp;
         x[w * S + i] = 0;
     }
@@ -386,7 +389,7 @@ __global__ void __launch_bounds__(256, 3) ntt_final_leaves_kernel(NttPass p) {
     cp_async_wait_all();
     __syncthreads();
     LoadFix<F> fix = {(const E *)p.scale_table, p.in_user_repr != 0};  // scale: single-pass LDE (q == 0), row = position
-    dif_stages<F, false>(x, roots_s, lp, F::W_LOG, 1, S, fix);
+    dif_stages<F, false>(x, roots_s, lp, wl, 1, S, fix);
     // frequency f sits at position bitrev(f), and the leaf order wants row offset bitrev(f): rows are positions.
     const u32 dq = chunk_to_natural(q, p.lp1, p.lp2);
     const u32 rq = lc ? (__brev(dq) >> (32 - lc)) : 0;
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(256, 3) ntt_final_leaves_kernel(NttPass p) {
     {
         // a thread keeps its column and walks down the rows (block size is a multiple of W): one shared load, the
         // representation change and one store per element, pointers advanced by constants
-        const u32 w = threadIdx.x & (W - 1), pp0 = threadIdx.x >> F::W_LOG, step = blockDim.x >> F::W_LOG;
+        const u32 w = threadIdx.x & (W - 1), pp0 = threadIdx.x >> wl, step = blockDim.x >> wl;
         if (w < ncols) {
             const E *sm = x + w * S + pp0;
             E *out = rows + (size_t)pp0 * p.dst_col_stride + w;
@@ -454,7 +457,8 @@ static void launch_pass_t(int kind, const NttPass &p, cudaStream_t stream, uint6
     const u32 lp = p.log_np, np = 1u << lp;
     if (kind == NTT_STRIDED) {
         u32 lmo = p.log_min - lp;
-        u32 lw = lmo < (u32)F::W_LOG ? lmo : (u32)F::W_LOG;
+        u32 wl = tile_width_log(F::W_LOG, lp);
+        u32 lw = lmo < wl ? lmo : wl;
         size_t smem = (((size_t)np << lw) + (np >> 1)) * sizeof(E);
         u64 tiles_per_col = ((u64)1 << (lmo - lw)) << (p.log_n - p.log_min);
         static bool attr_set = false;
@@ -465,7 +469,8 @@ static void launch_pass_t(int kind, const NttPass &p, cudaStream_t stream, uint6
         ntt_strided_kernel<F><<<(unsigned)(tiles_per_col * p.num_cols), block_threads((u64)np << lw), smem, stream>>>(p);
     } else if (kind == NTT_FINAL_NATURAL) {
         u32 lc = p.log_n - lp;
-        u32 lw = lc < (u32)F::W_LOG ? lc : (u32)F::W_LOG;
+        u32 wl = tile_width_log(F::W_LOG, lp);
+        u32 lw = lc < wl ? lc : wl;
         size_t smem = ((size_t)(np + F::PAD) * (1u << lw) + (np >> 1)) * sizeof(E);
         u64 groups = (u64)1 << (lc - lw);
         static bool attr_set = false;
@@ -476,14 +481,15 @@ static void launch_pass_t(int kind, const NttPass &p, cudaStream_t stream, uint6
         ntt_final_natural_kernel<F><<<(unsigned)(groups * p.num_cols), block_threads((u64)np << lw), smem, stream>>>(p);
     } else {
         u32 lc = p.log_n - lp;
-        size_t smem = ((size_t)(np + F::PAD) * (1u << F::W_LOG) + (np >> 1)) * sizeof(E);
-        u64 col_groups = (p.num_cols + (1u << F::W_LOG) - 1) >> F::W_LOG;
+        u32 wl = tile_width_log(F::W_LOG, lp);
+        size_t smem = ((size_t)(np + F::PAD) * (1u << wl) + (np >> 1)) * sizeof(E);
+        u64 col_groups = (p.num_cols + (1u << wl) - 1) >> wl;
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(ntt_final_leaves_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr_set = true;
         }
-        ntt_final_leaves_kernel<F><<<(unsigned)(col_groups << lc), block_threads((u64)np << F::W_LOG), smem, stream>>>(p);
+        ntt_final_leaves_kernel<F><<<(unsigned)(col_groups << lc), block_threads((u64)np << wl), smem, stream>>>(p);
     }
     ++*launches;
 }

@@ -291,7 +291,14 @@ int get_pass_table(p2g_ctx *ctx, const FieldInfo &f, int kind, unsigned log_min,
 
 // split log_n into at most three tile sizes, each <= MAX_TILE_LOG, as evenly as possible
 void plan_passes(unsigned log_n, unsigned lps[3], unsigned *num) {
-    unsigned P = log_n <= MAX_TILE_LOG ? 1 : (log_n <= 2 * MAX_TILE_LOG ? 2 : 3);
+    // test hook: P2G_TEST_MAX_TILE_LOG=k (1 <= k <= MAX_TILE_LOG) forces smaller tiles, so that the two- and three-pass
+    // plans can be exercised at sizes the CPU oracle checks in seconds
+    unsigned max_tile = MAX_TILE_LOG;
+    if (const char *e = getenv("P2G_TEST_MAX_TILE_LOG")) {
+        int k = atoi(e);
+        if (k >= 1 && k <= (int)MAX_TILE_LOG) max_tile = (unsigned)k;
+    }
+    unsigned P = log_n <= max_tile ? 1 : (log_n <= 2 * max_tile ? 2 : 3);
     unsigned rem = log_n;
     for (unsigned i = 0; i < P; i++) {
         unsigned take = (rem + (P - i) - 1) / (P - i);
@@ -300,6 +307,12 @@ void plan_passes(unsigned log_n, unsigned lps[3], unsigned *num) {
     }
     for (unsigned i = P; i < 3; i++) lps[i] = 0;
     *num = P;
+}
+
+static bool multi_pass(unsigned log_n) {  // the strided passes of a forward transform need the scratch buffer
+    unsigned lps[3], P;
+    plan_passes(log_n, lps, &P);
+    return P > 1;
 }
 
 // Runs one size-2^log_n transform over `num_cols` columns.
@@ -593,7 +606,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         }
         if (d->input_kind == P2G_INPUT_VALUES)
             if ((rc = ensure(ctx, ctx->coeffs, (size_t)c * col_bytes))) return rc;
-        if (L > MAX_TILE_LOG)
+        if (multi_pass(L))
             if ((rc = ensure(ctx, ctx->tmp, (size_t)c * col_bytes))) return rc;
     }
     // a kept batch owns fresh device buffers instead of borrowing the context's workspace
@@ -1111,7 +1124,7 @@ int32_t p2g_fri_begin(p2g_ctx *ctx, int32_t field, int32_t hash, int32_t repr_in
     } else {
         // lde_polynomial_values = lde_polynomial_coeffs.coset_fft(F::generator()) (fri/oracle.rs:226-231), computed here,
         // straight into bit-reversed order
-        if (log_n > MAX_TILE_LOG && (rc = ensure(ctx, ctx->tmp, bytes))) return rc;
+        if (multi_pass(log_n) && (rc = ensure(ctx, ctx->tmp, bytes))) return rc;
         if ((rc = run_transform(ctx, f, repr, false, log_n, degree, s->coeffs, ctx->tmp.ptr, s->values, degree, f.generator, 0))) return rc;
     }
     CK(cudaGetLastError());
@@ -1216,7 +1229,7 @@ int32_t p2g_fri_fold(p2g_ctx *ctx, p2g_fri *s, const void *beta) {
             if (cudaMemcpyAsync((char *)nv + k * f.elem, (char *)nc + k * f.elem, f.elem, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
                 rc = ctx->fail(P2G_ERR_CUDA, "copy failed");
     } else {
-        if (log_out > MAX_TILE_LOG) rc = ensure(ctx, ctx->tmp, (size_t)n_out * D * f.elem);
+        if (multi_pass(log_out)) rc = ensure(ctx, ctx->tmp, (size_t)n_out * D * f.elem);
         // coset_fft(shift): D base-field transforms, written as rows of D in bit-reversed order = the next leaf matrix
         if (!rc) rc = run_transform(ctx, f, s->repr, false, log_out, D, nc, ctx->tmp.ptr, nv, D, shift, 0);
     }
@@ -1375,7 +1388,7 @@ int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, u
         size_t out_bytes = (size_t)num_cols * N * f.elem;
         if ((rc = ensure(ctx, ctx->leaves, out_bytes))) return rc;
         if ((rc = ensure(ctx, ctx->misc, out_bytes))) return rc;
-        if (log_n > MAX_TILE_LOG)
+        if (multi_pass(log_n))
             if ((rc = ensure(ctx, ctx->tmp, in_bytes))) return rc;
         const uint64_t wN = two_adic_generator(f, log_n + rate_bits);
         for (unsigned b = 0; b < (1u << rate_bits); b++) {

@@ -10,7 +10,13 @@
 namespace p2g {
 
 enum FieldId { FIELD_GL = 0, FIELD_BB = 1 };
-enum { MAX_TILE_LOG = 10 };  // a CTA transforms at most 2^10 points per column segment in shared memory
+// A CTA transforms at most 2^MAX_TILE_LOG points per column segment in shared memory.  Tiles of up to 2^WIDE_TILE_LOG
+// points carry the field's full run width (64-byte runs: 8 Goldilocks / 16 BabyBear columns or offsets); a 2^11-point
+// tile halves it (32-byte runs, one DRAM sector) to stay at 64 KB, which makes 2^21 and 2^22 two-pass transforms.
+enum { MAX_TILE_LOG = 11, WIDE_TILE_LOG = 10 };
+static inline __host__ __device__ unsigned tile_width_log(unsigned field_wlog, unsigned log_np) {
+    return log_np > WIDE_TILE_LOG ? field_wlog - (log_np - WIDE_TILE_LOG) : field_wlog;
+}
 enum { POW_DIGIT_LOG = 10, POW_DIGIT = 1 << POW_DIGIT_LOG, POW_LEVELS = 3 };
 
 // ---- hash.cu -----------------------------------------------------------------------------------

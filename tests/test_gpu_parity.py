@@ -362,8 +362,9 @@ def test_config3_babybear_reduced_rows(ctx, oracle):
     _check_commit_properties(ctx, oracle, 1, 20, 256, 3, 4)
 
 
-def test_three_pass_ntt_plan(ctx, oracle):
-    """log n = 21, 22 use three NTT passes (tile sizes 7/7/7, 8/7/7): full parity on a few columns."""
+def test_wide_tile_two_pass_ntt_plan(ctx, oracle):
+    """log n = 21, 22 are two-pass transforms with 2^11-point tiles (11/10, 11/11; half-width runs): full parity on a few
+    columns."""
     import plonky2_goldibear_b200 as p2g
     for field, log_n in ((0, 21), (1, 22)):
         F = fields()[field]
@@ -373,6 +374,25 @@ def test_three_pass_ntt_plan(ctx, oracle):
         assert (np.stack(batch.polynomials) == ref["coeffs"]).all()
         assert (batch.merkle_tree.leaves == ref["leaves"]).all()
         assert (batch.merkle_tree.cap.hashes == ref["cap"]).all() and (batch.merkle_tree.digests == ref["digests"]).all()
+
+
+@pytest.mark.parametrize("max_tile,field,log_n,c", [(3, 0, 9, 9), (4, 1, 11, 17), (5, 0, 13, 3), (2, 1, 6, 20), (6, 0, 12, 8)])
+def test_three_pass_ntt_plan_forced_small_tiles(ctx, oracle, max_tile, field, log_n, c):
+    """The three-pass plan (2^23 rows and up in production) forced at small sizes through the library's test hook
+    P2G_TEST_MAX_TILE_LOG: inverse NTT, coset LDE, leaf order and tree bit-exact against the oracle."""
+    import os
+    import plonky2_goldibear_b200 as p2g
+    F = fields()[field]
+    vals = synthetic_columns(F.order, F.dtype, c, 1 << log_n, seed=100 + log_n)
+    ref = oracle.commit(field, vals, oracle.VALUES, 2, 3)
+    os.environ["P2G_TEST_MAX_TILE_LOG"] = str(max_tile)
+    try:
+        batch = p2g.PolynomialBatch.from_values(F, list(vals), 2, False, 3, ctx=ctx)
+    finally:
+        del os.environ["P2G_TEST_MAX_TILE_LOG"]
+    assert (np.stack(batch.polynomials) == ref["coeffs"]).all()
+    assert (batch.merkle_tree.leaves == ref["leaves"]).all()
+    assert (batch.merkle_tree.cap.hashes == ref["cap"]).all() and (batch.merkle_tree.digests == ref["digests"]).all()
 
 
 # ---- device-resident batch (SURVEY 8f N2): get / prove / get_lde_values served from GPU memory ---------------------
