@@ -94,6 +94,23 @@ struct LoadFix {
         if (scale) v = F::mul(v, scale[row]);
         return v;
     }
+    // the same for the R rows base + (j << shift) of one register-blocked unit: the factors are fetched through one
+    // per-thread pointer, a batch ahead of the multiplications
+    template <u32 R>
+    __device__ __forceinline__ void unit(typename F::E (&v)[R], u32 base, u32 shift) const {
+        if (user_repr) {
+#pragma unroll
+            for (u32 j = 0; j < R; j++) v[j] = F::load_user(v[j]);
+        }
+        if (scale) {
+            const typename F::E *sp = scale + base;
+            typename F::E f[R];
+#pragma unroll
+            for (u32 j = 0; j < R; j++) f[j] = __ldg(sp + (j << shift));
+#pragma unroll
+            for (u32 j = 0; j < R; j++) v[j] = F::mul(v[j], f[j]);
+        }
+    }
 };
 
 // Decimation-in-frequency butterflies over 2^lw interleaved transforms of np = 2^lp points held in shared memory,
@@ -126,10 +143,7 @@ __device__ __forceinline__ void dif_round(typename F::E *x, const typename F::E 
         E v[R];
 #pragma unroll
         for (u32 j = 0; j < R; j++) v[j] = base[j * stride];
-        if (FIRST) {
-#pragma unroll
-            for (u32 j = 0; j < R; j++) v[j] = fix(v[j], p0 + (j << lowbits));
-        }
+        if (FIRST) fix.template unit<R>(v, p0, lowbits);
 #pragma unroll
         for (int q = 0; q < K; q++) {
             const u32 hj = R >> (q + 1);  // distance between butterfly partners, in j
