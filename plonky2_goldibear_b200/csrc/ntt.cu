@@ -41,8 +41,12 @@ struct NttBb {
     typedef u32 E;
     static const int W_LOG = 4;  // 16 x 4 B = 64-byte runs
     static const int PAD = 4;    // keeps every padded row 16-byte aligned for cp.async
-    static __device__ __forceinline__ E load_user(E x) { return MONTY ? BbDev::from_monty(x) : BbDev::from_canonical(x); }
-    static __device__ __forceinline__ E store_user(E x) { return MONTY ? x : BbDev::to_canonical(x); }
+    // The transforms are linear and every twiddle / coset factor / scale is a Montgomery-form constant, so
+    // mul(word, constant) = word * constant in the WORD's own representation: canonical words go through the passes as
+    // canonical words and Montgomery words as Montgomery words -- no conversion on the way in or out, only the range
+    // fix that lets any u32 in (two conditional subtractions).  (The hash kernels, which are not linear, do convert.)
+    static __device__ __forceinline__ E load_user(E x) { return BbDev::from_monty(x); }
+    static __device__ __forceinline__ E store_user(E x) { return x; }
     static __device__ __forceinline__ E mul(E a, E b) { return bb_mul(a, b); }
     static __device__ __forceinline__ E add(E a, E b) { return bb_add(a, b); }
     static __device__ __forceinline__ E sub(E a, E b) { return bb_sub(a, b); }
