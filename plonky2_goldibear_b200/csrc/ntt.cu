@@ -22,6 +22,10 @@
 // first LDE pass) come from a per-pass table indexed exactly like the store, so they are read in the same 64-byte
 // runs; the remaining coset factor s^(m*i) is one small per-row table.  Both are built once per (field, size, coset)
 // by a kernel from three-level 1024-entry power tables and cached in the context.
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "p2g_internal.h"
 
 namespace p2g {
@@ -469,6 +473,18 @@ static unsigned block_threads(u64 tile_elems) {
     return (unsigned)(t < 64 ? 64 : (t > 256 ? 256 : t));
 }
 
+// opt a kernel into > 48 KB of dynamic shared memory, once per (kernel, device): the attribute is per device and one
+// process may drive several
+static void allow_large_smem(const void *kernel) {
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.insert(std::make_pair(kernel, dev)).second)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+}
+
 template <class F>
 static void launch_pass_t(int kind, const NttPass &p, cudaStream_t stream, uint64_t *launches) {
     typedef typename F::E E;
@@ -479,11 +495,7 @@ static void launch_pass_t(int kind, const NttPass &p, cudaStream_t stream, uint6
         u32 lw = lmo < wl ? lmo : wl;
         size_t smem = (((size_t)np << lw) + (np >> 1)) * sizeof(E);
         u64 tiles_per_col = ((u64)1 << (lmo - lw)) << (p.log_n - p.log_min);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(ntt_strided_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            attr_set = true;
-        }
+        allow_large_smem((const void *)ntt_strided_kernel<F>);
         ntt_strided_kernel<F><<<(unsigned)(tiles_per_col * p.num_cols), block_threads((u64)np << lw), smem, stream>>>(p);
     } else if (kind == NTT_FINAL_NATURAL) {
         u32 lc = p.log_n - lp;
@@ -491,22 +503,14 @@ static void launch_pass_t(int kind, const NttPass &p, cudaStream_t stream, uint6
         u32 lw = lc < wl ? lc : wl;
         size_t smem = ((size_t)(np + F::PAD) * (1u << lw) + (np >> 1)) * sizeof(E);
         u64 groups = (u64)1 << (lc - lw);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(ntt_final_natural_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            attr_set = true;
-        }
+        allow_large_smem((const void *)ntt_final_natural_kernel<F>);
         ntt_final_natural_kernel<F><<<(unsigned)(groups * p.num_cols), block_threads((u64)np << lw), smem, stream>>>(p);
     } else {
         u32 lc = p.log_n - lp;
         u32 wl = tile_width_log(F::W_LOG, lp);
         size_t smem = ((size_t)(np + F::PAD) * (1u << wl) + (np >> 1)) * sizeof(E);
         u64 col_groups = (p.num_cols + (1u << wl) - 1) >> wl;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(ntt_final_leaves_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            attr_set = true;
-        }
+        allow_large_smem((const void *)ntt_final_leaves_kernel<F>);
         ntt_final_leaves_kernel<F><<<(unsigned)(col_groups << lc), block_threads((u64)np << wl), smem, stream>>>(p);
     }
     ++*launches;
