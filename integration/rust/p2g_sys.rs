@@ -3,6 +3,13 @@
 #[repr(C)] pub struct p2g_ctx { _private: [u8; 0] }
 #[repr(C)] pub struct p2g_batch { _private: [u8; 0] }
 
+pub const P2G_FLAG_DEVICE_INPUT: u32 = 1;
+pub const P2G_FLAG_DEVICE_OUTPUT: u32 = 2;
+pub const P2G_FLAG_NO_LEAVES_OUT: u32 = 4;
+pub const P2G_FLAG_KEEP_ON_DEVICE: u32 = 8;
+pub const P2G_FLAG_LEAVES_ONLY: u32 = 16;   // commit split over column ranges: stop after the leaves
+pub const P2G_FLAG_LEAVES_READY: u32 = 32;  // ... and build the tree over a finished leaf matrix
+
 #[repr(C)]
 pub struct p2g_commit_desc {
     pub field: i32, pub hash: i32, pub repr: i32, pub input_kind: i32,

@@ -66,3 +66,19 @@ def test_product_does_not_touch_the_oracle():
                 assert "p2o" not in text and "oracle/" not in text and "import oracle" not in text, os.path.join(dirpath, f)
     out = subprocess.run(["ldd", os.path.join(pkg, "libp2g_cuda.so")], capture_output=True, text=True).stdout
     assert "libp2o" not in out
+
+
+def test_flag_constants_match_header():
+    """Every P2G_FLAG_* the header defines has the same value in the ctypes mirror (the Rust p2g-sys file follows the same
+    list, integration/rust/p2g_sys.rs)."""
+    from plonky2_goldibear_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "p2g.h")).read()
+    flags = dict(re.findall(r"#define\s+P2G_(FLAG_[A-Z_]+)\s+(\d+)u", hdr))
+    assert len(flags) >= 6
+    for name, value in flags.items():
+        assert getattr(_lib, name) == int(value), name
+    vals = sorted(int(v) for v in flags.values())
+    assert vals == [1 << i for i in range(len(vals))], "flags must stay distinct bits"
+    rust = open(os.path.join(ROOT, "integration", "rust", "p2g_sys.rs")).read()
+    for name, value in flags.items():
+        assert re.search(r"pub const P2G_%s: u32 = %s;" % (name, value), rust), "p2g_sys.rs lacks P2G_" + name
