@@ -198,3 +198,14 @@ def test_commit_definition(oracle, field, p, c):
     # from_coeffs on the coefficients gives the same tree
     res2 = oracle.commit(field, res["coeffs"], oracle.COEFFS, r, h)
     assert (res2["cap"] == res["cap"]).all() and (res2["leaves"] == res["leaves"]).all()
+
+
+@pytest.mark.parametrize("field,log_n,lps", [(0, 6, [3, 3]), (0, 8, [3, 3, 2]), (1, 7, [4, 3]), (1, 5, [1, 2, 2])])
+def test_decimation_in_time_lde_model_matches_the_leaf_order(field, log_n, lps):
+    """tools/ct_lde_model.py -- the index arithmetic of the next NTT design (twiddles that absorb the coset factor, data in
+    place between passes) -- reproduces every coset block of the oracle's from_coeffs leaves."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import ct_lde_model
+    assert ct_lde_model.check(field, log_n, lps)
