@@ -106,3 +106,51 @@ def test_pipelined_exchange_column_groups_cover_every_column_once():
         assert sorted(seen) == list(range(c))
     groups, _ = column_groups(135, 8, 8)
     assert groups == [(0, 64), (64, 128), (128, 135)]
+
+
+def _group_worker(rank, world, port, log_n, c, r, h, tile, out_dir):
+    """bench.py --exchange pipelined on CPU: the columns cross in groups; after the barrier of group s every rank extends
+    exactly that column range into its leaf rows (P2G_FLAG_LEAVES_ONLY), and the tree follows when all are in."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle import p2o
+    from plonky2_goldibear_b200.sharding import column_groups, plan
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 1 << log_n
+    sp = plan(rank, world, c, log_n, r, h)
+    groups, owned = column_groups(c, world, tile)
+    gather = np.zeros((c, n), dtype=np.uint64)          # this rank's gather buffer, original column order
+    leaves = np.zeros((sp.row_end - sp.row_begin, c), dtype=np.uint64)
+    for s, (glo, ghi) in enumerate(groups):
+        lo, hi = owned[rank][s]
+        mine = synthetic_columns(GL_P, np.uint64, hi - lo, n, col_begin=lo) if hi > lo else np.zeros((0, n), dtype=np.uint64)
+        share = np.stack([p2o.ifft(p2o.GL, v) for v in mine]) if hi > lo else mine
+        parts = [None] * world
+        dist.all_gather_object(parts, (lo, hi, share))   # the fused epilogue's peer stores + the group's barrier
+        for plo, phi, block in parts:
+            gather[plo:phi] = block
+        # LDE of this group only, written into its column range of the leaf matrix
+        ext = p2o.commit(p2o.GL, gather[glo:ghi], p2o.COEFFS, r, 0)["leaves"][sp.row_begin:sp.row_end]
+        leaves[:, glo:ghi] = ext
+    digests, cap = p2o.merkle_tree(p2o.GL, leaves, sp.local_cap_height)
+    np.savez(os.path.join(out_dir, "grank%d.npz" % rank), rows=leaves, digests=digests, cap=cap,
+             plan=np.array([sp.digest_begin, sp.digest_end, sp.cap_begin, sp.cap_end]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_pipelined_exchange_by_column_groups(tmp_path, oracle):
+    world, log_n, c, r, h, tile = 2, 5, 11, 2, 2, 2
+    port = _free_port()
+    mp.spawn(_group_worker, args=(world, port, log_n, c, r, h, tile, str(tmp_path)), nprocs=world, join=True)
+    vals = synthetic_columns(GL_P, np.uint64, c, 1 << log_n)
+    ref = oracle.commit(oracle.GL, vals, oracle.VALUES, r, h)
+    parts = [np.load(os.path.join(str(tmp_path), "grank%d.npz" % i)) for i in range(world)]
+    assert (np.concatenate([p["rows"] for p in parts]) == ref["leaves"]).all()
+    for p in parts:
+        db, de, cb, ce = [int(x) for x in p["plan"]]
+        assert (ref["digests"][db:de] == p["digests"]).all()
+        assert (ref["cap"][cb:ce] == p["cap"]).all()
