@@ -191,7 +191,8 @@ int get_pow_table(p2g_ctx *ctx, const FieldInfo &f, uint64_t base, const void **
     return 0;
 }
 
-// w^k for k < 2^(lp-1), w the primitive 2^lp-th root (or its inverse)
+// In-tile twiddles of a 2^lp-point tile, w the primitive 2^lp-th root (or its inverse).  BabyBear: w^k, k < 2^(lp-1).
+// Goldilocks: [2^lp][4], entry k = w^k * 2^(24 i), i < 4 -- the four W_i a limb join multiplies by (gl_limbs.cuh)
 int get_root_table(p2g_ctx *ctx, const FieldInfo &f, unsigned lp, bool inverse, const void **out) {
     auto key = std::make_pair(f.id, ((uint64_t)inverse << 8) | lp);
     auto it = ctx->root_tables.find(key);
@@ -199,14 +200,27 @@ int get_root_table(p2g_ctx *ctx, const FieldInfo &f, unsigned lp, bool inverse, 
         *out = it->second;
         return 0;
     }
-    size_t cnt = lp ? ((size_t)1 << (lp - 1)) : 1;
+    const bool gl = f.id == FIELD_GL;
+    size_t cnt = gl ? ((size_t)4 << lp) : (lp ? ((size_t)1 << (lp - 1)) : 1);
     std::vector<unsigned char> host(cnt * f.elem);
     uint64_t w = two_adic_generator(f, lp);
     if (inverse) w = f_inv(f, w);
     uint64_t cur = 1;
-    for (size_t k = 0; k < cnt; k++) {
-        store_elem(f, host.data(), k, f_internal(f, cur));
-        cur = f_mul(f, cur, w);
+    if (gl) {
+        const uint64_t x24 = (uint64_t)1 << 24;
+        for (size_t k = 0; k < ((size_t)1 << lp); k++) {
+            uint64_t v = cur;
+            for (int i = 0; i < 4; i++) {
+                store_elem(f, host.data(), 4 * k + i, v);
+                v = f_mul(f, v, x24);
+            }
+            cur = f_mul(f, cur, w);
+        }
+    } else {
+        for (size_t k = 0; k < cnt; k++) {
+            store_elem(f, host.data(), k, f_internal(f, cur));
+            cur = f_mul(f, cur, w);
+        }
     }
     void *d = nullptr;
     CK(cudaMalloc(&d, host.size()));
@@ -315,19 +329,22 @@ static bool multi_pass(unsigned log_n) {  // the strided passes of a forward tra
     return P > 1;
 }
 
-// Runs one size-2^log_n transform over `num_cols` columns.
-//   inverse: values -> coefficients (natural order, scaled by 1/n), result in `dst` (column-major, user repr)
-//   forward: coset LDE block: coefficients (user repr, `src`) scaled by powers of `shift`, rows written to the
-//            leaf matrix `dst` starting at row_base.
-// `src` is overwritten when inverse (the strided passes run in place); forward uses `tmp` for the strided passes.
-int run_transform(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsigned log_n, unsigned num_cols,
-                  void *src, void *tmp, void *dst, uint64_t dst_stride, uint64_t shift, uint64_t row_base,
-                  void *const *peer_dst = nullptr, unsigned num_peers = 0) {
+// Runs size-2^log_n transforms over `num_cols` columns.
+//   inverse: values -> coefficients (natural order, scaled by 1/n), result in `dst` (column-major, user repr); nb = 1
+//   forward: nb coset LDE blocks in one launch per pass: coefficients (user repr, `src`) scaled by powers of
+//            shifts[b], rows written to the leaf matrix `dst` starting at row_base + b * row_stride.
+// `src` is overwritten when inverse (the strided passes run in place); forward uses `tmp` for the strided passes
+// (nb * num_cols * n elements).
+int run_transform_batch(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsigned log_n, unsigned num_cols,
+                        void *src, void *tmp, void *dst, uint64_t dst_stride, const uint64_t *shifts, unsigned nb,
+                        uint64_t row_base, uint64_t row_stride, void *const *peer_dst = nullptr, unsigned num_peers = 0) {
     unsigned lps[3], P;
     plan_passes(log_n, lps, &P);
     const uint64_t n = (uint64_t)1 << log_n;
+    if (nb == 0 || nb > 8 || (inverse && nb != 1)) return ctx->fail(P2G_ERR_INVALID, "bad transform batch %u", nb);
     unsigned log_min = log_n;
     const void *cur_src = src;
+    uint64_t cur_src_batch_stride = 0;
     void *stage_buf = inverse ? src : tmp;
     for (unsigned i = 0; i < P; i++) {
         NttPass p;
@@ -336,27 +353,33 @@ int run_transform(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsi
         p.log_n = log_n;
         p.log_min = log_min;
         p.log_np = lps[i];
+        p.inverse = inverse;
+        p.gl_eps = 0xffffffffu;
+        p.num_batch = nb;
         int rc = get_root_table(ctx, f, lps[i], inverse, &p.roots);
         if (rc) return rc;
         p.src = cur_src;
         p.src_col_stride = n;
-        p.async_ok = ((uintptr_t)cur_src % 16 == 0) && ((n * f.elem) % 16 == 0 || num_cols == 1);
+        p.src_batch_stride = cur_src_batch_stride;
+        p.async_ok = ((uintptr_t)cur_src % 16 == 0) && ((n * f.elem) % 16 == 0 || (num_cols == 1 && nb == 1));
         p.in_user_repr = (i == 0);
         if (i == 0 && !inverse) {
             // coset factor s^j, j = i*m_out + j0: the row part s^(m_out*i) on load, s^j0 merged into the pass table
-            rc = get_pass_table(ctx, f, 1, log_min, lps[i], 0, shift, &p.scale_table);
-            if (rc) return rc;
+            for (unsigned b = 0; b < nb; b++)
+                if ((rc = get_pass_table(ctx, f, 1, log_min, lps[i], 0, shifts[b], &p.scale_tables[b]))) return rc;
         }
         if (i + 1 < P) {
             // strided pass with inter-pass twiddles w_{m_in}^(f*j0)
             uint64_t w = two_adic_generator(f, log_min);
             if (inverse) w = f_inv(f, w);
-            rc = get_pass_table(ctx, f, 0, log_min, lps[i], w, (i == 0 && !inverse) ? shift : 0, &p.tw_table);
-            if (rc) return rc;
+            for (unsigned b = 0; b < nb; b++)
+                if ((rc = get_pass_table(ctx, f, 0, log_min, lps[i], w, (i == 0 && !inverse) ? shifts[b] : 0, &p.tw_tables[b]))) return rc;
             p.dst = stage_buf;
             p.dst_col_stride = n;
+            p.dst_batch_stride = (uint64_t)num_cols * n;
             launch_ntt_pass(f.id, repr, NTT_STRIDED, p, ctx->stream, &ctx->launches);
             cur_src = stage_buf;
+            cur_src_batch_stride = (uint64_t)num_cols * n;
             log_min -= lps[i];
         } else {
             p.lp1 = P >= 2 ? lps[0] : 0;
@@ -367,11 +390,18 @@ int run_transform(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsi
             if (inverse) {
                 for (unsigned k = 0; k < num_peers && k < 8; k++) p.peer_dst[k] = peer_dst[k];
                 p.num_peers = num_peers;
-                p.use_final_scale = 1;
-                p.final_scale = f_internal(f, f_pow(f, f_inv(f, 2), log_n));  // n^-1 = (1/2)^lg n, fft.rs:78
+                const uint64_t n_inv = f_pow(f, f_inv(f, 2), log_n);  // n^-1 = (1/2)^lg n, fft.rs:78
+                if (f.id == FIELD_GL) {
+                    // n^-1 is a power of two here: it rides in the last round's join (gl_limbs.cuh) for free
+                    for (int k = 0; k < 4; k++) p.join_w[k] = f_mul(f, n_inv, f_pow(f, 2, 24 * k));
+                } else {
+                    p.use_final_scale = 1;
+                    p.final_scale = f_internal(f, n_inv);
+                }
                 launch_ntt_pass(f.id, repr, NTT_FINAL_NATURAL, p, ctx->stream, &ctx->launches);
             } else {
                 p.row_base = row_base;
+                p.row_batch_stride = row_stride;
                 launch_ntt_pass(f.id, repr, NTT_FINAL_LEAVES, p, ctx->stream, &ctx->launches);
             }
         }
@@ -379,6 +409,26 @@ int run_transform(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsi
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return ctx->fail(P2G_ERR_CUDA, "NTT launch failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+int run_transform(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsigned log_n, unsigned num_cols,
+                  void *src, void *tmp, void *dst, uint64_t dst_stride, uint64_t shift, uint64_t row_base,
+                  void *const *peer_dst = nullptr, unsigned num_peers = 0) {
+    return run_transform_batch(ctx, f, repr, inverse, log_n, num_cols, src, tmp, dst, dst_stride, &shift, 1, row_base, 0,
+                               peer_dst, num_peers);
+}
+
+// how many cosets one LDE launch carries: as many as the scratch buffer of the strided passes allows (it holds the
+// first pass' output of every coset in flight).  P2G_LDE_BATCH overrides (experiments).
+unsigned lde_batch(unsigned log_n, unsigned cosets, size_t bytes_per_coset) {
+    unsigned nb = 1;
+    const size_t cap = (size_t)10 << 30;
+    while (nb * 2 <= cosets && nb * 2 <= 8 && (!multi_pass(log_n) || (size_t)(nb * 2) * bytes_per_coset <= cap)) nb *= 2;
+    if (const char *e = getenv("P2G_LDE_BATCH")) {
+        int k = atoi(e);
+        if (k >= 1 && k <= 8) nb = std::min<unsigned>((unsigned)k, cosets);
+    }
+    return nb ? nb : 1;
 }
 
 int check_field_hash(p2g_ctx *ctx, int field, int hash, const FieldInfo **out) {
@@ -606,8 +656,6 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         }
         if (d->input_kind == P2G_INPUT_VALUES)
             if ((rc = ensure(ctx, ctx->coeffs, (size_t)c * col_bytes))) return rc;
-        if (multi_pass(L))
-            if ((rc = ensure(ctx, ctx->tmp, (size_t)c * col_bytes))) return rc;
     }
     // a kept batch owns fresh device buffers instead of borrowing the context's workspace
     p2g_batch *batch = nullptr;
@@ -745,6 +793,23 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     }
     // cosets transformed inside the per-group loop (see below); 5/8 of them balance a group's transforms against its upload
     const unsigned early_cosets = pipelined ? std::max(1u, cosets_local * 5 / 8) : cosets_local;
+    // several cosets share one launch per pass (the coefficients are then read from DRAM once per batch); the scratch
+    // buffer of the strided passes holds the first pass' output of every coset in flight
+    const unsigned nb_group = lde_batch(L, early_cosets, (size_t)std::min(group_cols, c) * col_bytes);
+    const unsigned nb_all = lde_batch(L, cosets_local - early_cosets ? cosets_local - early_cosets : 1, (size_t)c * col_bytes);
+    if (multi_pass(L))
+        if ((rc = ensure(ctx, ctx->tmp, std::max((size_t)nb_group * std::min(group_cols, c), (size_t)nb_all * c) * col_bytes))) return rc;
+    auto lde_cosets = [&](unsigned b_begin, unsigned b_end, unsigned nb, unsigned ncol, void *coeffs, void *leaves) -> int {
+        for (unsigned b = b_begin; b < b_end; b += nb) {
+            const unsigned cur = std::min(nb, b_end - b);
+            uint64_t shifts[8];
+            for (unsigned k = 0; k < cur; k++) shifts[k] = f_mul(f, g, f_pow(f, wN, bitrev(coset0 + b + k, r)));
+            int rc2 = run_transform_batch(ctx, f, repr, false, L, ncol, coeffs, ctx->tmp.ptr, leaves, pitch_dev, shifts, cur,
+                                          (uint64_t)b * n, n);
+            if (rc2) return rc2;
+        }
+        return 0;
+    };
     for (unsigned gi2 = 0; gi2 < num_groups; gi2++) {
         const unsigned col0 = gi2 * group_cols, ncol = std::min(group_cols, c - col0);
         char *g_in = (char *)d_input + (size_t)col0 * col_bytes;
@@ -777,12 +842,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         // one coset of n rows at a time, written straight into leaf order.  Only the first `early_cosets` of them
         // here: that much transform work hides under the upload of the next column group; the rest follows below,
         // coset by coset, so that finished cosets can start their way home while later ones are still computed.
-        for (unsigned b = 0; b < early_cosets; b++) {
-            uint64_t shift = f_mul(f, g, f_pow(f, wN, bitrev(coset0 + b, r)));
-            if ((rc = run_transform(ctx, f, repr, false, L, ncol, g_co, (char *)ctx->tmp.ptr + (size_t)col0 * col_bytes,
-                                    (char *)d_leaves + (size_t)col0 * f.elem, pitch_dev, shift, (uint64_t)b * n)))
-                return rc;
-        }
+        if ((rc = lde_cosets(0, early_cosets, nb_group, ncol, g_co, (char *)d_leaves + (size_t)col0 * f.elem))) return rc;
         CK(cudaEventRecord(ctx->tev[3 * gi2 + 2], st));
     }
     const bool leaves_early = overlap_d2h && want_leaves && !salt && cosets_local <= 62 && is_pinned(d->leaves_out);
@@ -801,11 +861,15 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     if (leaves_early)
         for (unsigned b = 0; b < early_cosets; b++)
             if ((rc = send_coset(b))) return rc;
-    for (unsigned b = early_cosets; b < cosets_local; b++) {
-        uint64_t shift = f_mul(f, g, f_pow(f, wN, bitrev(coset0 + b, r)));
-        // every column is on the device by now: one launch per pass over all of them
-        if ((rc = run_transform(ctx, f, repr, false, L, c, d_coeffs, ctx->tmp.ptr, d_leaves, pitch_dev, shift, (uint64_t)b * n))) return rc;
-        if (leaves_early && (rc = send_coset(b))) return rc;
+    // every column is on the device by now: one launch per pass over all of them.  When finished cosets travel home
+    // during the computation they are transformed one at a time, so that each can leave as soon as it is complete.
+    for (unsigned b = early_cosets; b < cosets_local;) {
+        const unsigned cur = leaves_early ? 1 : std::min(nb_all, cosets_local - b);
+        if ((rc = lde_cosets(b, b + cur, cur, c, d_coeffs, d_leaves))) return rc;
+        if (leaves_early)
+            for (unsigned k = 0; k < cur; k++)
+                if ((rc = send_coset(b + k))) return rc;
+        b += cur;
     }
     const bool leaves_sent = leaves_early;
     if (salt)
@@ -832,6 +896,9 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     }
 
     // ---- "build Merkle tree"
+    // (Running the leaf sponge of finished cosets on a second, low-priority stream under the transforms of the next
+    // ones was measured: 136.7 against 134.7 ms per 2^20 x 135 commit -- the two kernels do not share an SM's issue
+    // slots productively.)
     TreeShape tree = {tree_log, cap_local, d_digests, d_cap};
     launch_leaf_hash(f.id, repr, d_leaves, pitch_dev, width, 0, rows_local, tree, st, &ctx->launches);
     CK(cudaEventRecord(ctx->ev[6], st));
@@ -1388,12 +1455,16 @@ int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, u
         size_t out_bytes = (size_t)num_cols * N * f.elem;
         if ((rc = ensure(ctx, ctx->leaves, out_bytes))) return rc;
         if ((rc = ensure(ctx, ctx->misc, out_bytes))) return rc;
+        const unsigned cosets = 1u << rate_bits, nb = lde_batch(log_n, cosets, in_bytes);
         if (multi_pass(log_n))
-            if ((rc = ensure(ctx, ctx->tmp, in_bytes))) return rc;
+            if ((rc = ensure(ctx, ctx->tmp, (size_t)nb * in_bytes))) return rc;
         const uint64_t wN = two_adic_generator(f, log_n + rate_bits);
-        for (unsigned b = 0; b < (1u << rate_bits); b++) {
-            uint64_t shift = f_mul(f, f.generator, f_pow(f, wN, bitrev(b, rate_bits)));
-            if ((rc = run_transform(ctx, f, repr, false, log_n, num_cols, ctx->in.ptr, ctx->tmp.ptr, ctx->leaves.ptr, num_cols, shift, (uint64_t)b * n)))
+        for (unsigned b = 0; b < cosets; b += nb) {
+            uint64_t shifts[8];
+            const unsigned cur = std::min(nb, cosets - b);
+            for (unsigned k = 0; k < cur; k++) shifts[k] = f_mul(f, f.generator, f_pow(f, wN, bitrev(b + k, rate_bits)));
+            if ((rc = run_transform_batch(ctx, f, repr, false, log_n, num_cols, ctx->in.ptr, ctx->tmp.ptr, ctx->leaves.ptr, num_cols,
+                                          shifts, cur, (uint64_t)b * n, n)))
                 return rc;
         }
         void *dst = dev_out ? out : ctx->misc.ptr;

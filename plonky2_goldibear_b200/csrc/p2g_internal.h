@@ -63,24 +63,34 @@ struct NttPass {
     uint32_t log_min;      // chunk length at this level (log_n for the first pass)
     uint32_t log_np;       // points transformed per tile
     uint32_t lp1, lp2;     // tile sizes of the earlier passes (digit sizes of the chunk index), 0 if unused
-    const void *roots;     // w_{np}^k, k < np/2 (direction specific), internal representation
-    const void *tw_table;     // strided pass: [m_in] inter-pass factors, entry f*m_out + j0 = w_{m_in}^(f*j0) (* s^j0 on
-                              // the first LDE pass); same index as the store, so it is read in the same 64-byte runs
-    const void *scale_table;  // [np] coset factors s^(m_out * i) applied to tile row i on load, or null
-    uint64_t final_scale;  // internal representation; multiplied into the outputs of a final pass when use_final_scale
+    const void *roots;     // direction specific, internal representation: Goldilocks w_{np}^k for k < np (the limb
+                           // joins look up w * 2^(24 i) = w_{np}^(k + i * step) in the same table), BabyBear k < np/2
+    // One launch can carry several LDE cosets ("batch"): CTAs of the same tile and different cosets are adjacent in
+    // the grid, so the coefficient tile they all read comes from DRAM once and from L2 after that.
+    uint32_t num_batch;        // >= 1
+    uint64_t src_batch_stride; // elements between the batch entries' inputs (0: all read the same input)
+    uint64_t dst_batch_stride; // elements between their outputs (column-major outputs)
+    uint64_t row_batch_stride; // leaf output: rows between their blocks
+    const void *tw_tables[8];     // strided pass, per batch entry: [m_in] inter-pass factors, entry f*m_out + j0 =
+                                  // w_{m_in}^(f*j0) (* s^j0 on the first LDE pass); indexed like the store
+    const void *scale_tables[8];  // per batch entry: [np] coset factors s^(m_out * i) applied to tile row i on load, or null
+    uint64_t final_scale;  // BabyBear: internal representation of 1/n, multiplied into the outputs of a final natural pass
     uint32_t use_final_scale;
-    uint64_t row_base;     // leaf output: first row of this coset
+    uint64_t join_w[4];    // Goldilocks final natural pass: n^-1 * 2^(24 i) mod p, the scale rides in the last join
+    uint64_t row_base;     // leaf output: first row of batch entry 0
     // final natural pass of a column-sharded inverse transform: the coefficients are also written into the gather
     // buffers of the other GPUs (peer pointers mapped over NVLink), i.e. the all-gather is fused into the epilogue
     void *peer_dst[8];
     uint32_t num_peers;
-    uint32_t async_ok;       // src base and column stride are 16-byte aligned: the tile may be staged with cp.async
+    uint32_t async_ok;       // src base and column stride are 16-byte aligned: vector / asynchronous tile loads
     uint32_t in_user_repr;   // 1: src is in the caller's representation (load conversion), 0: internal
     uint32_t out_user_repr;  // 1: dst is in the caller's representation (canonical / chosen repr)
+    uint32_t inverse;        // direction (selects the kernels' compile-time roots of unity)
+    uint32_t gl_eps;         // 0xffffffff (Goldilocks 2^32 - 1), a run-time operand on purpose: see gl_limbs.cuh fold96
 };
 enum NttKind { NTT_STRIDED = 0, NTT_FINAL_NATURAL = 1, NTT_FINAL_LEAVES = 2 };
 void launch_ntt_pass(int field, int repr, int kind, const NttPass &p, cudaStream_t stream, uint64_t *launches);
-// fills tw_table / scale_table entries from three-level power tables ([3][1024], base^(k*1024^level)):
+// fills tw_tables / scale_tables entries from three-level power tables ([3][1024], base^(k*1024^level)):
 //   tw_table[f*m_out + j0] = wpow^(f*j0) * (spow ? spow^j0 : 1);   scale_table[i] = spow^(i << log_mout)
 void launch_build_tw_table(int field, void *out, uint32_t log_min, uint32_t log_np, const void *wpow, const void *spow,
                            cudaStream_t stream, uint64_t *launches);

@@ -38,3 +38,16 @@ def test_cpp_mirror_matches_oracle(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     assert "host mirror ok" in res.stdout
+
+
+def test_ntt_tile_code_on_the_host_matches_the_definition(tmp_path):
+    """The headers the NTT kernels are built from (gl_limbs / ntt_tile / ntt_kinds .cuh), compiled with g++ and run
+    thread by thread: every round plan (tile sizes 2^0 .. 2^11), one-, two- and three-pass transforms, both directions,
+    both fields, coset batching and the bit-reversed leaf order, against a naive O(n^2) evaluation."""
+    src = os.path.join(ROOT, "tests", "cpp", "ntt_tile_emul_test.cpp")
+    exe = str(tmp_path / "ntt_tile_emul_test")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-Wno-attributes", "-I", cuda_inc, src, "-o", exe], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-4000:]
+    assert "all ok" in res.stdout and "FAIL" not in res.stdout
