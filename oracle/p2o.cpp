@@ -511,6 +511,41 @@ static void permute(uint32_t s[W]) {  // run_once :609-671 without the wire writ
         external(s);
     }
 }
+// The witness of one Poseidon2BabyBearGate operation (num_ops = 1), wire order of gates/poseidon2_babybear.rs:79-147:
+// inputs 0..15, outputs 16..31, swap 32, delta 33..40, S-box inputs of full rounds 1..3 (41..88), of the 13 partial
+// rounds (89..101), of full rounds 4..7 (102..165).  Follows the generator run_once :573-680 with the permutation
+// code above, so that tests can substitute the oracle's round-by-round states into the gate's constraint equations
+// (eval_unfiltered :204-309), the reference's second in-tree definition of the permutation.
+enum { GATE_WIRES = 166 };
+static void gate_wires(const uint32_t in[W], uint32_t swap, uint32_t wires[GATE_WIRES]) {
+    uint32_t s[W];
+    for (unsigned i = 0; i < W; i++) wires[i] = s[i] = in[i];
+    wires[32] = swap;
+    for (unsigned i = 0; i < 8; i++) wires[33 + i] = BB::mul(swap, BB::sub(s[i + 8], s[i]));  // :590-601
+    if (swap == 1)
+        for (unsigned i = 0; i < 8; i++) std::swap(s[i], s[i + 8]);  // :603-607
+    external(s);
+    for (unsigned r = 0; r < 4; r++) {
+        for (unsigned i = 0; i < W; i++) s[i] = BB::add(s[i], P2O_BB_P2_EXTERNAL_RC[r][i]);
+        if (r != 0)
+            for (unsigned i = 0; i < W; i++) wires[41 + 16 * (r - 1) + i] = s[i];  // wire_full_sbox_0
+        for (unsigned i = 0; i < W; i++) s[i] = sbox(s[i]);
+        external(s);
+    }
+    for (unsigned r = 0; r < 13; r++) {
+        s[0] = BB::add(s[0], P2O_BB_P2_INTERNAL_RC[r]);
+        wires[89 + r] = s[0];  // wire_partial_sbox
+        s[0] = sbox(s[0]);
+        internal(s);
+    }
+    for (unsigned r = 4; r < 8; r++) {
+        for (unsigned i = 0; i < W; i++) s[i] = BB::add(s[i], P2O_BB_P2_EXTERNAL_RC[r][i]);
+        for (unsigned i = 0; i < W; i++) wires[102 + 16 * (r - 4) + i] = s[i];  // wire_full_sbox_1
+        for (unsigned i = 0; i < W; i++) s[i] = sbox(s[i]);
+        external(s);
+    }
+    for (unsigned i = 0; i < W; i++) wires[16 + i] = s[i];
+}
 }  // namespace p2bb
 
 // ------------------------------------------------------------------------------------------------
@@ -878,6 +913,7 @@ uint64_t p2o_inv(int field, uint64_t a) { return field == P2O_FIELD_GL ? f_inv<G
 void p2o_poseidon_gl(uint64_t s[12]) { pgl::permute_fast(s); }
 void p2o_poseidon_gl_naive(uint64_t s[12]) { pgl::permute_naive(s); }
 void p2o_poseidon2_bb(uint32_t s[16]) { p2bb::permute(s); }
+void p2o_poseidon2_bb_gate_wires(const uint32_t in[16], uint32_t swap, uint32_t wires[166]) { p2bb::gate_wires(in, swap, wires); }
 
 void p2o_fft(int field, void *data, unsigned log_n, unsigned zero_factor) {
     if (field == P2O_FIELD_GL)

@@ -69,6 +69,8 @@ uint64_t p2o_inv(int field, uint64_t a);
 void p2o_poseidon_gl(uint64_t state[12]);        /* fast form, poseidon_goldilocks.rs:912-922 */
 void p2o_poseidon_gl_naive(uint64_t state[12]);  /* naive form, poseidon_goldilocks.rs:927-948 */
 void p2o_poseidon2_bb(uint32_t state[16]);
+/* witness of one Poseidon2BabyBearGate operation, wire order of gates/poseidon2_babybear.rs:79-147 (num_ops = 1) */
+void p2o_poseidon2_bb_gate_wires(const uint32_t in[16], uint32_t swap, uint32_t wires[166]);
 
 /* transforms, in place on one column of 2^log_n elements */
 void p2o_fft(int field, void *data, unsigned log_n, unsigned zero_factor); /* fft_with_options(.., Some(zero_factor), None) */

@@ -55,6 +55,8 @@ def load(native: bool = False) -> ctypes.CDLL:
     for name in ("p2o_poseidon_gl", "p2o_poseidon_gl_naive", "p2o_poseidon2_bb"):
         getattr(lib, name).argtypes = [vp]
         getattr(lib, name).restype = None
+    lib.p2o_poseidon2_bb_gate_wires.argtypes = [vp, ui, vp]
+    lib.p2o_poseidon2_bb_gate_wires.restype = None
     lib.p2o_fft.argtypes = [ci, vp, ui, ui]
     lib.p2o_ifft.argtypes = [ci, vp, ui]
     lib.p2o_coset_fft.argtypes = [ci, vp, ui, u64, ui]
@@ -98,6 +100,15 @@ def permute(field: int, state: np.ndarray, naive: bool = False) -> np.ndarray:
     else:
         lib.p2o_poseidon2_bb(s.ctypes.data)
     return s
+
+
+def poseidon2_bb_gate_wires(state: np.ndarray, swap: int = 0) -> np.ndarray:
+    """The 166 wires of one Poseidon2BabyBearGate operation on `state` (gates/poseidon2_babybear.rs:79-147, :573-680)."""
+    lib = load()
+    s = np.ascontiguousarray(state, dtype=np.uint32)
+    wires = np.zeros(166, dtype=np.uint32)
+    lib.p2o_poseidon2_bb_gate_wires(s.ctypes.data, int(swap), wires.ctypes.data)
+    return wires
 
 
 def fft(field, col, zero_factor=0):
