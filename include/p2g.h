@@ -102,8 +102,10 @@ typedef struct {
                                so the RNG stays on the Rust side */
     uint32_t flags;         /* P2G_FLAG_* */
     const void *const *col_ptrs;  /* [num_cols] host pointers, n elements each */
-    const void *const *salt_ptrs; /* [num_salt_cols] host pointers, N elements each, natural (un-bit-reversed)
-                                     LDE order exactly like the reference's extra lde_values columns */
+    const void *const *salt_ptrs; /* [num_salt_cols] pointers, N elements each, natural (un-bit-reversed) LDE order
+                                     exactly like the reference's extra lde_values columns.  HOST or DEVICE memory,
+                                     independently of P2G_FLAG_DEVICE_INPUT (which describes col_ptrs only): the
+                                     upload resolves its direction from each pointer */
     void *const *coeffs_out; /* [num_cols] host pointers (n each) receiving `polynomials`; may alias col_ptrs;
                                 NULL to skip (from_coeffs callers already own them) */
     void *leaves_out;        /* [N][leaf_pitch] row-major; NULL with P2G_FLAG_NO_LEAVES_OUT */

@@ -149,8 +149,18 @@ int ensure(p2g_ctx *ctx, Buffer &b, size_t bytes) {
     }
     if (bytes == 0) return 0;
     cudaError_t e = cudaMalloc(&b.ptr, bytes);
+    if (e != cudaSuccess && !ctx->pool.empty()) {
+        // buffers of freed device-resident batches are only parked: give them back and try once more
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &pb : ctx->pool) cudaFree(pb.ptr);
+        ctx->pool.clear();
+        ctx->pool_bytes = 0;
+        e = cudaMalloc(&b.ptr, bytes);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
+        b.ptr = nullptr;
         return ctx->fail(P2G_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
     }
     b.bytes = bytes;
@@ -456,6 +466,14 @@ bool is_pinned(const void *p) {
     return a.type == cudaMemoryTypeHost;
 }
 
+// every buffer of a pointer table (a table mixing pinned and pageable buffers takes the plain path)
+bool all_pinned(const void *const *ptrs, unsigned count) {
+    if (!ptrs || !count) return false;
+    for (unsigned j = 0; j < count; j++)
+        if (!is_pinned(ptrs[j])) return false;
+    return true;
+}
+
 unsigned ilog2(uint64_t x) {
     unsigned l = 0;
     while (((uint64_t)1 << l) < x) l++;
@@ -649,6 +667,17 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
 
     const size_t col_bytes = n * f.elem;
     cudaStream_t st = ctx->stream;
+    // an error return must not leave copies in flight that still reference the caller's host buffers
+    struct StreamGuard {
+        p2g_ctx *c;
+        bool ok;
+        ~StreamGuard() {
+            if (ok) return;
+            cudaStreamSynchronize(c->stream);
+            cudaStreamSynchronize(c->copy_stream);
+            cudaStreamSynchronize(c->h2d_stream);
+        }
+    } stream_guard{ctx, false};
     // ---- workspace
     if (!leaves_ready) {
         if (!dev_in || d->input_kind == P2G_INPUT_VALUES) {
@@ -740,6 +769,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         d->stage_seconds[3] = ev_seconds(ctx->ev[3], ctx->ev[4]);
         d->kernel_seconds[2] = ev_seconds(ctx->ev[3], ctx->ev[6]);
         d->kernel_seconds[3] = ev_seconds(ctx->ev[6], ctx->ev[4]);
+        stream_guard.ok = true;
         return P2G_OK;
     }
 
@@ -752,14 +782,14 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     const bool overlap_d2h = !dev_out;
     const bool values = d->input_kind == P2G_INPUT_VALUES;
     const unsigned tile_cols = f.id == FIELD_GL ? 8 : 16;
-    bool pipelined = !dev_in && c > 2 * tile_cols && is_pinned(d->col_ptrs[0]) && is_pinned(d->col_ptrs[c - 1]);
+    bool pipelined = !dev_in && c > 2 * tile_cols && all_pinned(d->col_ptrs, c);
     unsigned group_cols = c;
     if (pipelined) {
         group_cols = 2 * tile_cols;
         while ((c + group_cols - 1) / group_cols > p2g_ctx::MAX_GROUPS) group_cols += 2 * tile_cols;
     }
     const unsigned num_groups = (c + group_cols - 1) / group_cols;
-    const bool coeffs_early = overlap_d2h && values && d->coeffs_out && is_pinned(d->coeffs_out[0]) && is_pinned(d->coeffs_out[c - 1]);
+    const bool coeffs_early = overlap_d2h && values && d->coeffs_out && all_pinned(d->coeffs_out, c);
     const bool coeffs_sent = coeffs_early;
     // from_coeffs into a kept batch: the coefficients land directly in the batch's own buffer
     void *h2d_base = (keep && !values) ? batch->coeffs : ctx->in.ptr;
@@ -779,8 +809,9 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     if (salt) {
         if ((rc = ensure(ctx, ctx->salts, (size_t)salt * N * f.elem))) return rc;
         for (unsigned j = 0; j < salt; j++)
-            CK(cudaMemcpyAsync((char *)ctx->salts.ptr + (size_t)j * N * f.elem, d->salt_ptrs[j], N * f.elem,
-                               dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+            // host or device pointers alike (the Rust shim draws its salts on the host even when the columns are
+            // already device resident): the runtime resolves the direction from the pointer
+            CK(cudaMemcpyAsync((char *)ctx->salts.ptr + (size_t)j * N * f.elem, d->salt_ptrs[j], N * f.elem, cudaMemcpyDefault, st));
     }
     void *d_coeffs = d_input;
     if (values) d_coeffs = keep ? batch->coeffs : ((dev_out && d->coeffs_out && d->coeffs_out[0]) ? d->coeffs_out[0] : ctx->coeffs.ptr);
@@ -892,6 +923,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         d->kernel_seconds[0] = d->stage_seconds[0];
         d->kernel_seconds[1] = d->stage_seconds[1];
         d->kernel_seconds[2] = d->kernel_seconds[3] = 0.0;
+        stream_guard.ok = true;
         return P2G_OK;
     }
 
@@ -948,6 +980,7 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         *d->batch_out = batch;
         batch = nullptr;  // ownership passes to the caller
     }
+    stream_guard.ok = true;
     return P2G_OK;
 }
 

@@ -77,7 +77,7 @@ class PolynomialBatch:
     def _commit(cls, field, columns, input_kind, rate_bits, blinding, cap_height, timing, ctx=None,
                 repr: int = REPR_CANONICAL, salts: Optional[Sequence[np.ndarray]] = None, rng=None,
                 shard_index: int = 0, shard_count: int = 0, want_leaves: bool = True, pinned_out: bool = False,
-                keep_on_device: bool = False):
+                keep_on_device: bool = False, leaf_pitch: int = 0):
         ctx = ctx or _lib.default_context()
         if len(columns) == 0:
             raise IndexError("index out of bounds: the len is 0 but the index is 0")  # polynomials[0], oracle.rs:101
@@ -107,12 +107,15 @@ class PolynomialBatch:
         alloc = ctx.pinned_empty if pinned_out else (lambda shape, dtype: np.empty(shape, dtype=dtype))
         if keep_on_device:
             want_leaves = False
-        leaves = alloc((rows, width), field.dtype) if want_leaves else None
+        pitch = leaf_pitch or width
+        if pitch < width:
+            raise ValueError("leaf_pitch smaller than the leaf length")
+        leaves = alloc((rows, pitch), field.dtype) if want_leaves else None
         digests = None if keep_on_device else alloc((max(2 * (rows - (1 << cap_local)), 0), d), field.dtype)
         cap = np.empty((1 << cap_local, d), dtype=field.dtype)
         coeffs = None
         if input_kind == INPUT_VALUES and not keep_on_device:
-            coeffs = list(np.empty((len(cols), degree), dtype=field.dtype))  # one block: adjacent columns come back in one copy
+            coeffs = list(alloc((len(cols), degree), field.dtype))  # one block: adjacent columns come back in one copy
 
         desc = _lib.CommitDesc()
         desc.field, desc.hash, desc.repr, desc.input_kind = field.field_id, field.hash_id, repr, input_kind
@@ -132,7 +135,7 @@ class PolynomialBatch:
             out_ptrs = _ptr_array(coeffs)
             desc.coeffs_out = ctypes.cast(out_ptrs, ctypes.POINTER(ctypes.c_void_p))
         desc.leaves_out = leaves.ctypes.data if leaves is not None else None
-        desc.leaf_pitch = width
+        desc.leaf_pitch = pitch
         desc.digests_out = digests.ctypes.data if digests is not None and digests.size else None
         desc.cap_out = cap.ctypes.data
         desc.shard_index, desc.shard_count = shard_index, shard_count
@@ -149,7 +152,7 @@ class PolynomialBatch:
             tree = DeviceMerkleTree(field, ctx, handle, MerkleCap(cap))
             polys = None if input_kind == INPUT_VALUES else cols  # coefficients stay on the device (download on demand)
         else:
-            tree = MerkleTree(field, leaves, digests, MerkleCap(cap))
+            tree = MerkleTree(field, leaves[:, :width] if leaves is not None and pitch != width else leaves, digests, MerkleCap(cap))
         batch = cls(field, polys, tree, degree_log, rate_bits, blinding)
         batch.desc = desc
         batch.wall_seconds = wall

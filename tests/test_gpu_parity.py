@@ -519,3 +519,86 @@ def test_commit_split_over_column_ranges(ctx, oracle, field, log_n, c, r, h, g, 
 def ctx_commit_shard(ctx, F, vals, r, h, shard, g):
     import plonky2_goldibear_b200 as p2g
     return p2g.PolynomialBatch.from_values(F, list(vals), r, False, h, ctx=ctx, shard_index=shard, shard_count=g)
+
+
+@pytest.mark.parametrize("field,log_n,c,r,h,kind,g,pitch_extra", [
+    (0, 11, 41, 3, 4, "values", 1, 0), (0, 11, 41, 3, 4, "coeffs", 1, 3), (0, 12, 19, 3, 2, "values", 8, 0),
+    (1, 11, 70, 3, 4, "values", 1, 2), (1, 12, 40, 2, 3, "coeffs", 4, 0), (0, 10, 135, 3, 4, "values", 2, 1)])
+def test_pinned_pipelined_commit_matches_oracle(ctx, oracle, field, log_n, c, r, h, kind, g, pitch_extra):
+    """The end-to-end headline path: PINNED host columns (more than two tiles of them) take the pipelined route of
+    p2g_commit -- column groups uploaded on the h2d stream under the transforms of the previous group, coefficients and
+    finished cosets sent home early on the copy stream.  Everything that comes back (coefficients, leaves at a pitch,
+    digests, cap) must equal the oracle's, also when the same context is reused: a wrong event order would return stale
+    host leaves or coefficients under a correct (device-computed) cap."""
+    import plonky2_goldibear_b200 as p2g
+    F = fields()[field]
+    n = 1 << log_n
+    vals = synthetic_columns(F.order, F.dtype, c, n, seed=77 + c)
+    pinned = ctx.pinned_empty((c, n), F.dtype)
+    for rep in range(3):
+        if rep:
+            vals = synthetic_columns(F.order, F.dtype, c, n, seed=1000 + rep)
+        pinned[...] = vals
+        okind = oracle.VALUES if kind == "values" else oracle.COEFFS
+        ref = oracle.commit(field, vals, okind, r, h)
+        lg = g.bit_length() - 1
+        rows_local = (n << r) // g
+        for shard in range(g if rep == 0 else 1):
+            fn = p2g.PolynomialBatch.from_values if kind == "values" else p2g.PolynomialBatch.from_coeffs
+            b = fn(F, list(pinned), r, False, h, ctx=ctx, pinned_out=True, leaf_pitch=c + pitch_extra,
+                   shard_index=shard if g > 1 else 0, shard_count=g if g > 1 else 0)
+            r0 = shard * rows_local
+            assert (b.merkle_tree.leaves == ref["leaves"][r0:r0 + rows_local]).all()
+            if kind == "values":
+                assert (np.stack(b.polynomials) == ref["coeffs"]).all()
+            if g == 1:
+                assert (b.merkle_tree.digests == ref["digests"]).all()
+                assert (b.merkle_tree.cap.hashes == ref["cap"]).all()
+            elif h >= lg:
+                per = (1 << h) // g
+                assert (b.merkle_tree.cap.hashes == ref["cap"][shard * per:(shard + 1) * per]).all()
+                nd = len(ref["digests"]) // g
+                assert (b.merkle_tree.digests == ref["digests"][shard * nd:(shard + 1) * nd]).all()
+
+
+@pytest.mark.parametrize("field,log_n,c", [(0, 10, 11), (1, 9, 20)])
+def test_device_input_with_host_salts(ctx, oracle, field, log_n, c):
+    """P2G_FLAG_DEVICE_INPUT + blinding: the columns are device resident, the salt columns come from the HOST (the RNG
+    stays on the caller's side, fri/oracle.rs:144-148) -- the salt upload resolves its direction from the pointer."""
+    import ctypes
+    import torch
+    from plonky2_goldibear_b200 import _lib
+    F = fields()[field]
+    r, h = 3, 2
+    n, N = 1 << log_n, 1 << (log_n + r)
+    vals = synthetic_columns(F.order, F.dtype, c, n, seed=5)
+    salts = synthetic_columns(F.order, F.dtype, 4, N, seed=6)
+    ref = oracle.commit(field, vals, oracle.VALUES, r, h, salts=salts)
+    ndt = np.int64 if field == 0 else np.int32
+    d_vals = torch.from_numpy(np.ascontiguousarray(vals).view(ndt)).cuda()
+    width = c + 4
+    d_el = F.num_hash_out_elts
+    leaves = np.empty((N, width), dtype=F.dtype)
+    digests = np.empty((2 * (N - (1 << h)), d_el), dtype=F.dtype)
+    cap = np.empty((1 << h, d_el), dtype=F.dtype)
+    coeffs = np.empty((c, n), dtype=F.dtype)
+    for salts_on_device in (False, True):
+        d = _lib.CommitDesc()
+        d.field, d.hash, d.repr, d.input_kind = F.field_id, F.hash_id, 0, 0
+        d.log_n, d.num_cols, d.rate_bits, d.cap_height = log_n, c, r, h
+        d.num_salt_cols = 4
+        d.flags = _lib.FLAG_DEVICE_INPUT
+        col = (ctypes.c_void_p * 1)(d_vals.data_ptr())
+        d.col_ptrs = ctypes.cast(col, ctypes.POINTER(ctypes.c_void_p))
+        d_salts = torch.from_numpy(np.ascontiguousarray(salts).view(ndt)).cuda() if salts_on_device else None
+        sp = (ctypes.c_void_p * 4)(*[(d_salts.data_ptr() + j * N * F.elem_bytes) if salts_on_device else salts[j].ctypes.data
+                                     for j in range(4)])
+        d.salt_ptrs = ctypes.cast(sp, ctypes.POINTER(ctypes.c_void_p))
+        outp = (ctypes.c_void_p * c)(*[coeffs[j].ctypes.data for j in range(c)])
+        d.coeffs_out = ctypes.cast(outp, ctypes.POINTER(ctypes.c_void_p))
+        d.leaves_out, d.leaf_pitch = leaves.ctypes.data, width
+        d.digests_out, d.cap_out = digests.ctypes.data, cap.ctypes.data
+        leaves[...] = 0
+        ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(d)))
+        assert (leaves == ref["leaves"]).all() and (digests == ref["digests"]).all() and (cap == ref["cap"]).all()
+        assert (coeffs == ref["coeffs"]).all()
