@@ -35,6 +35,15 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def host_cores():
+    """Threads the CPU arm uses: every core this process may run on.  Asked for explicitly -- torchrun exports
+    OMP_NUM_THREADS=1 to its ranks, which would otherwise turn the CPU arm into a single-thread run."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -113,7 +122,8 @@ def run_reference(args, field_name):
     fid = p2o.GL if field_name == "gl" else p2o.BB
     order, dtype = p2o.ORDER[fid], p2o.DTYPE[fid]
     log_n = min(args.log_n, args.cpu_sample_log_n)
-    cores = p2o.load(native).p2o_max_threads()
+    p2o.load(native)
+    cores = host_cores()
     vals = synthetic_columns(order, dtype, args.cols, 1 << log_n)
     times, stages = [], None
     for i in range(args.warmup + args.steps):
@@ -128,14 +138,45 @@ def run_reference(args, field_name):
     value = (args.cols << log_n) / t
     sample = "2^%d x %d of the 2^%d x %d workload per step (rate_bits=%d, cap_height=%d)" % (
         log_n, args.cols, args.log_n, args.cols, args.rate_bits, args.cap_height)
+    # the whole workload once, so that the per-step sample's throughput is checked against the full size it stands for
+    full = None
+    if log_n < args.log_n and not args.no_full_check:
+        es = 8 if field_name == "gl" else 4
+        need = args.cols * (1 << args.log_n) * es * (3 + 2 * (1 << args.rate_bits)) * 1.2  # input, coeffs, LDE columns, leaves
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = None
+        if avail is not None and avail < need:
+            full = {"skipped": "needs ~%.0f GB of host memory, %.0f GB available" % (need / 1e9, avail / 1e9)}
+        else:
+            try:
+                del vals
+                big = np.empty((args.cols, 1 << args.log_n), dtype=dtype)
+                for cb in range(0, args.cols, 8):
+                    ce = min(cb + 8, args.cols)
+                    big[cb:ce] = synthetic_columns(order, dtype, ce - cb, 1 << args.log_n, col_begin=cb)
+                t0 = time.perf_counter()
+                res = p2o.commit(fid, big, p2o.VALUES, args.rate_bits, args.cap_height, threads=cores, want_leaves=True, native=native)
+                dt = time.perf_counter() - t0
+                full = {"ms": dt * 1e3, "value": (args.cols << args.log_n) / dt, "unit": UNIT, "runs": 1,
+                        "ratio_to_sample": ((args.cols << args.log_n) / dt) / value,
+                        "stage_ms": {k: v * 1e3 for k, v in zip(("IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree"), res["stage_seconds"])}}
+                del res, big
+            except MemoryError as e:
+                full = {"skipped": "MemoryError: %s" % e}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64" if field_name == "gl" else "u32", "data": "synthetic",
         "config": workload_config(args, field_name),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "full_size_run": full,
                          "stage_ms": {k: v * 1e3 for k, v in zip(("IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree"), stages)},
-                         "note": "C++ restatement of the reference CPU path (oracle/), g++ -O3 %s -fopenmp; the Rust reference cannot be built here" % ("-march=native" if native else "-march=x86-64-v3")},
+                         "note": "C++ restatement of the reference CPU path (oracle/), g++ -O3 %s -fopenmp, %d threads = every core this "
+                                 "process may run on (OMP_NUM_THREADS is ignored: torchrun sets it to 1); the Rust reference cannot be built here" % (
+                                     "-march=native" if native else "-march=x86-64-v3", cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -155,7 +196,36 @@ def workload_config(args, field_name):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def run_ours(args, field_name):
+_REAL_STDOUT = [None]
+
+
+def link_ceilings(ctx, d_buf, h_buf, stream, barrier, dev, G, dist, torch):
+    """What the host link gives this job at best: every rank copies up to 1 GiB between pinned host memory and HBM at the
+    same time (one cudaMemcpyAsync per GPU on the library's stream), aggregate GB/s = total bytes / slowest rank."""
+    nbytes = int(min(1 << 30, d_buf.numel() * d_buf.element_size(), h_buf.nbytes))
+    out = {}
+    for name, kind, dst, src in (("d2h_ceiling_gbs", 1, h_buf.ctypes.data, d_buf.data_ptr()),
+                                 ("h2d_ceiling_gbs", 0, d_buf.data_ptr(), h_buf.ctypes.data)):
+        best = None
+        for _ in range(3):
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            ctx.check(ctx.lib.p2g_memcpy_async(ctx.handle, dst, src, nbytes, kind))
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+            if G > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t[0]) if best is None else min(best, float(t[0]))
+        out[name] = G * nbytes / (best * 1e-3) / 1e9
+    out["ceiling_note"] = "%d concurrent pinned copies of %d MiB, one per GPU, best of 3, max over ranks" % (G, nbytes >> 20)
+    return out
+
+
+def run_ours(args, field_name, check_only=False):
+    """check_only: one step of the same code path (same exchange, same buffers, same C-ABI calls) at a size the oracle
+    finishes in milliseconds, every output of every rank compared with the oracle; nothing is timed or printed."""
     import torch
     import torch.distributed as dist
     import plonky2_goldibear_b200 as p2g
@@ -167,16 +237,18 @@ def run_ours(args, field_name):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     # stdout carries exactly one JSON line: park the real stdout and send everything else (NCCL's version banner,
     # library chatter) to stderr until the line is printed
-    sys.stdout.flush()
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
+    if _REAL_STDOUT[0] is None:
+        sys.stdout.flush()
+        _REAL_STDOUT[0] = os.dup(1)
+        os.dup2(2, 1)
+    real_stdout = _REAL_STDOUT[0]
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus %d needs torchrun with one rank per GPU" % args.gpus)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the commit path has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     F = p2g.GOLDILOCKS if field_name == "gl" else p2g.BABYBEAR
     tdtype = torch.int64 if field_name == "gl" else torch.int32
@@ -411,15 +483,15 @@ def run_ours(args, field_name):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]) * 1e-3, float(t[1]) * 1e-3
 
-    for _ in range(args.warmup):
+    for _ in range(0 if check_only else args.warmup):
         device_step()
     kernel_s[:] = 0
     launches0 = ctx.kernel_launches() + (ctx2.kernel_launches() if pipelined else 0)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not check_only:
         sampler.start()
-    dev_total, _ = timed(device_step, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    dev_total, _ = timed(device_step, 1 if check_only else args.steps)
+    clocks = sampler.stop() if rank == 0 and not check_only else None
     launches = ctx.kernel_launches() + (ctx2.kernel_launches() if pipelined else 0) - launches0
     args.exchange = ("pipelined-ce" if ce_copies else "pipelined") if pipelined else (exchange if G > 1 else None)  # what actually ran
     t_step = dev_total / args.steps
@@ -428,6 +500,35 @@ def run_ours(args, field_name):
 
     # parity guard inside the bench: the cap of the timed run must equal the cap of the e2e (host) run below
     cap_dev = d_cap.cpu().numpy().view(F.dtype).copy()
+
+    ref = None
+    if check_only:
+        # the oracle's commit of the whole (small) job; this rank's slices of it
+        from oracle import p2o
+        fid = p2o.GL if field_name == "gl" else p2o.BB
+        ref = p2o.commit(fid, synthetic_columns(F.order, F.dtype, c, n), p2o.VALUES, r, h, threads=host_cores())
+        if h < lg:
+            raise SystemExit("parity check needs cap_height >= log2(gpus)")
+        nd, per_cap = len(ref["digests"]) // G, (1 << h) // G
+        exp = {"leaves": ref["leaves"][rank * rows_local:(rank + 1) * rows_local],
+               "digests": ref["digests"][rank * nd:(rank + 1) * nd],
+               "cap": ref["cap"][rank * per_cap:(rank + 1) * per_cap],
+               "coeffs": ref["coeffs"][col0:col1]}
+
+        def verdict(what, checks):
+            bad = [k for k, (got, want) in checks.items() if got.shape != want.shape or not (got == want).all()]
+            okt = torch.tensor([0 if bad else 1], device=dev)
+            if G > 1:
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            if bad:
+                log("PARITY FAILURE (%s, rank %d of %d): %s differ from the oracle" % (what, rank, G, ", ".join(bad)))
+            if int(okt) == 0:
+                raise SystemExit(3)
+
+        verdict("device-resident step over the %s exchange" % (args.exchange if G > 1 else "single-GPU path"), {
+            "leaves": (d_leaves.cpu().numpy().view(F.dtype), exp["leaves"]),
+            "digests": (d_digests.cpu().numpy().view(F.dtype)[:nd], exp["digests"]),
+            "cap": (cap_dev, exp["cap"])})
 
     # ---- end-to-end step: host (pinned) buffers in, every output back to the host
     e2e = None
@@ -457,7 +558,18 @@ def run_ours(args, field_name):
             ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(e_desc)))
 
         e2e_step()
+        barrier()
         assert (h_cap == cap_dev).all(), "device-resident and end-to-end runs disagree on the Merkle cap"
+        if check_only:
+            verdict("end-to-end step, host buffers", {
+                "leaves": (h_leaves, exp["leaves"]), "digests": (h_digests[:nd], exp["digests"]), "cap": (h_cap, exp["cap"]),
+                "coeffs": (h_coeffs[:col1 - col0], exp["coeffs"])})
+            if rank == 0:
+                log("parity check: 2^%d x %d over %d GPU(s), exchange %s -- device-resident and end-to-end outputs of every "
+                    "rank equal the oracle's" % (L, c, G, args.exchange))
+            ctx.close()
+            return
+        ceilings = link_ceilings(ctx, d_leaves, h_leaves, stream, barrier, dev, G, dist, torch)
         _, e2e_wall = timed(e2e_step, args.e2e_steps)
         te = e2e_wall / args.e2e_steps
         h2d = (col1 - col0) * n * es
@@ -468,13 +580,43 @@ def run_ours(args, field_name):
         e2e = {"value": (c << L) / te, "unit": UNIT, "h2d_bytes_per_step": int(tb[0]), "d2h_bytes_per_step": int(tb[1]),
                "ms_per_step": te * 1e3, "steps": args.e2e_steps,
                "note": "p2g_commit with pinned host buffers; all of coeffs, leaves, digests, cap copied back"}
+        e2e.update(ceilings)
+        if ceilings.get("d2h_ceiling_gbs"):
+            # what the host link alone allows: every output byte at the measured D2H ceiling (uploads overlap)
+            e2e["d2h_floor_ms"] = float(tb[1]) / (ceilings["d2h_ceiling_gbs"] * 1e9) * 1e3
+            e2e["frac_of_link_floor"] = e2e["d2h_floor_ms"] / (te * 1e3)
+
+    # ---- the same drop-in call with PAGEABLE buffers: what the unchanged Rust API hands over (Vec<F> from the allocator)
+    e2e_pageable = None
+    if not args.no_e2e and G == 1 and not check_only:
+        p_in = np.array(host_in[:c], copy=True)
+        p_coeffs = np.empty((c, n), dtype=F.dtype)
+        p_leaves = np.empty((rows_local, c), dtype=F.dtype)
+        p_digests = np.empty((max(2 * (rows_local - (1 << cap_local)), 1), d_el), dtype=F.dtype)
+        p_cap = np.empty((1 << cap_local, d_el), dtype=F.dtype)
+        pg = make_desc(0, 0)
+        pg.col_ptrs = ptrs([p_in[j].ctypes.data for j in range(c)])
+        pg.coeffs_out = ptrs([p_coeffs[j].ctypes.data for j in range(c)])
+        pg.leaves_out, pg.leaf_pitch = p_leaves.ctypes.data, c
+        pg.digests_out, pg.cap_out = p_digests.ctypes.data, p_cap.ctypes.data
+
+        def pageable_step():
+            ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(pg)))
+
+        pageable_step()
+        assert (p_cap == cap_dev).all() and (p_leaves[-1] == h_leaves[-1]).all(), "pageable run disagrees"
+        _, pw = timed(pageable_step, 2)
+        e2e_pageable = {"value": (c << L) / (pw / 2), "unit": UNIT, "ms_per_step": pw / 2 * 1e3, "steps": 2,
+                        "note": "the same call with pageable host buffers (what an unchanged Vec<F>-based caller hands over): "
+                                "every copy goes through the driver's staging buffers, nothing overlaps"}
+        del p_in, p_coeffs, p_leaves, p_digests
 
     # ---- device-resident variant of the same call (N2): inputs from pinned host memory, leaves / digests / coefficients
     # stay in HBM behind a batch handle, the cap comes back, then the prover's access pattern is served by gather kernels
     # (28 FRI queries: one row + one Merkle path each, fri/prover.rs:219-255).  Secondary number; `e2e` above is the
     # full drop-in with every output copied to the host.
     e2e_resident = None
-    if not args.no_e2e and G == 1:
+    if not args.no_e2e and G == 1 and not check_only:
         k_desc = make_desc(0, _lib.FLAG_KEEP_ON_DEVICE)
         k_desc.col_ptrs = ptrs([host_in[j].ctypes.data for j in range(c)])
         k_cap = np.empty((1 << h, d_el), dtype=F.dtype)
@@ -555,6 +697,7 @@ def run_ours(args, field_name):
         "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64" if field_name == "gl" else "u32", "data": "synthetic",
         "config": workload_config(args, field_name), "clocks": clocks, "e2e": e2e, "e2e_device_resident_outputs": e2e_resident,
+        "e2e_pageable": e2e_pageable,
         "gpu_launches": int(launches),
         "roofline": roofline, "roofline_ntt": roofline_ntt, "int_pipe": int_pipe,
         "stage_ms": {"inverse_ntt": ksec[0] * 1e3, "lde_ntt": ksec[1] * 1e3, "leaf_sponge": ksec[2] * 1e3, "tree_levels": ksec[3] * 1e3},
@@ -562,6 +705,11 @@ def run_ours(args, field_name):
     }
     if G == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, field_name)
+    if G == 1 and not args.no_latency:
+        try:
+            line["latency"] = latency_entries(field_name, ctx, p2g)
+        except Exception as e:
+            line["latency"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     if G == 1 and not args.no_fri:
         try:
             line["fri_commit_phase"] = fri_commit_phase_bench(args, field_name, ctx, p2g)
@@ -584,7 +732,8 @@ def cpu_baseline(args, field_name):
         native = False
     fid = p2o.GL if field_name == "gl" else p2o.BB
     log_n = min(args.log_n, args.cpu_sample_log_n)
-    cores = p2o.load(native).p2o_max_threads()
+    p2o.load(native)
+    cores = host_cores()
     vals = synthetic_columns(p2o.ORDER[fid], p2o.DTYPE[fid], args.cols, 1 << log_n)
     best, stages = None, None
     for _ in range(2):
@@ -599,6 +748,38 @@ def cpu_baseline(args, field_name):
                 log_n, args.cols, 1 << (args.log_n - log_n), cores),
             "ms": best * 1e3,
             "stage_ms": {k: v * 1e3 for k, v in zip(("IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree"), stages)}}
+
+
+def latency_entries(field_name, ctx, p2g):
+    """Latency-bound shapes of BASELINE configs 1 and 4: the four oracles of the fibonacci circuit
+    (2^4 rows) and of a 2^12-row recursion circuit, and a FRI layer tree of 32-element leaves.  Host wall clock around the
+    public call (pageable numpy columns in, every output back on the host), median of 30 after 5 warm-up calls."""
+    f = p2g.GOLDILOCKS if field_name == "gl" else p2g.BABYBEAR
+    rng = np.random.default_rng(11)
+    if field_name == "gl":
+        shapes = [(4, 85), (4, 135), (4, 20), (4, 16), (12, 85), (12, 135), (12, 20), (12, 16)]
+    else:
+        shapes = [(12, 46), (12, 167), (12, 36), (12, 48)]  # narrow BabyBear recursion config (SURVEY 8d row 4)
+    out = {"how": "host wall clock around PolynomialBatch.from_values / MerkleTree.new, pageable host arrays in and out, "
+                  "rate_bits 3, cap_height 4, median of 30 calls after 5 warm-up calls", "commit_ms": {}, "merkle_ms": {}}
+    for log_n, c in shapes:
+        cols = [rng.integers(0, f.order, size=1 << log_n, dtype=np.uint64).astype(f.dtype) for _ in range(c)]
+        ts = []
+        for it in range(35):
+            t0 = time.perf_counter()
+            p2g.PolynomialBatch.from_values(f, cols, 3, False, 4, ctx=ctx)
+            ts.append(time.perf_counter() - t0)
+        out["commit_ms"]["2^%d x %d" % (log_n, c)] = float(np.median(ts[5:])) * 1e3
+    d = f.extension_degree
+    for log_leaves, leaf_len in ((11, 16 * d), (7, 16 * d)):  # arity-16 layers of a 2^15 codeword (fri/prover.rs:104-108)
+        leaves = rng.integers(0, f.order, size=(1 << log_leaves, leaf_len), dtype=np.uint64).astype(f.dtype)
+        ts = []
+        for it in range(35):
+            t0 = time.perf_counter()
+            p2g.MerkleTree.new(f, leaves, min(4, log_leaves), ctx=ctx)
+            ts.append(time.perf_counter() - t0)
+        out["merkle_ms"]["2^%d leaves x %d"% (log_leaves, leaf_len)] = float(np.median(ts[5:])) * 1e3
+    return out
 
 
 def fri_commit_phase_bench(args, field_name, ctx, p2g):
@@ -666,6 +847,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fri", action="store_true", help="skip the secondary FRI commit-phase measurement")
     ap.add_argument("--cpu-sample-log-n", type=int, default=16)
+    ap.add_argument("--no-full-check", action="store_true",
+                    help="--impl reference: skip the single full-size run that checks the per-step sample's throughput")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="N > 1: skip the 2^12-row commit through the same exchange that is compared with the oracle before timing")
+    ap.add_argument("--no-latency", action="store_true", help="skip the small-shape latency entries (configs 1 and 4)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: timing rules ask for >= 3 warm-up steps; got %d" % args.warmup)
@@ -676,6 +862,12 @@ def main():
     if args.impl == "reference":
         run_reference(args, args.field)
     else:
+        if not args.no_parity_check:
+            # before anything is timed: the same path at 2^12 rows, every rank's outputs against the oracle
+            import copy
+            small = copy.copy(args)
+            small.log_n, small.steps, small.warmup, small.e2e_steps, small.no_e2e = min(12, args.log_n), 1, 0, 1, False
+            run_ours(small, args.field, check_only=True)
         run_ours(args, args.field)
 
 

@@ -357,9 +357,69 @@ def test_config2_full_size_goldilocks(ctx, oracle):
 
 
 def test_config3_babybear_reduced_rows(ctx, oracle):
-    """BASELINE config 3 shape (BabyBear, 256 columns, rate_bits 3, cap_height 4) at 2^20 rows -- the same three-pass
-    NTT plan class (log n > 20 needs it; 2^22 is exercised by bench.py --field bb) with 8.6 GB of leaves."""
+    """BASELINE config 3 shape (BabyBear, 256 columns, rate_bits 3, cap_height 4) at 2^20 rows, every output on the host
+    (8.6 GB of leaves); the full 2^22 rows are checked device-resident in the next test."""
     _check_commit_properties(ctx, oracle, 1, 20, 256, 3, 4)
+
+
+def test_config3_full_size_babybear_device_resident(ctx, oracle):
+    """BASELINE config 3 at its real size: BabyBear 2^22 x 256, rate_bits 3, cap_height 4 (34 GB of leaves, two-pass NTT
+    with 2^11-point tiles).  The outputs stay on the device (P2G_FLAG_KEEP_ON_DEVICE; the host would need 41 GB for
+    them); sampled rows, their Merkle paths and sampled coefficient columns come back through the batch accessors and
+    are checked against the definition: row k = P(g * w_N^bitrev(k)), the path hashes up to the cap with the oracle's
+    sponge / compression, and the CPU FFT of a returned coefficient column gives back the input column."""
+    import plonky2_goldibear_b200 as p2g
+    F = fields()[1]
+    p = F.order
+    log_n, c, r, h = 22, 256, 3, 4
+    n, N = 1 << log_n, 1 << (log_n + r)
+    vals = np.empty((c, n), dtype=F.dtype)
+    for cb in range(0, c, 8):
+        vals[cb:cb + 8] = synthetic_columns(p, F.dtype, 8, n, seed=3, col_begin=cb)
+    batch = p2g.PolynomialBatch.from_values(F, list(vals), r, False, h, ctx=ctx, keep_on_device=True)
+    tree = batch.merkle_tree
+    try:
+        lib = oracle.load()
+        rng = np.random.default_rng(22)
+        ks = [0, N - 1, n, n - 1] + [int(x) for x in rng.integers(0, N, size=4)]
+        rows = tree.get_many(ks)
+        sibs = tree.prove_many(ks)
+        assert rows.shape == (len(ks), c) and sibs.shape == (len(ks), log_n + r - h, F.num_hash_out_elts)
+        for row, sib, k in zip(rows, sibs, ks):
+            assert oracle.verify_merkle_proof_to_cap(1, row, k, tree.cap.hashes, sib)
+        coeffs = batch.download_polynomials()
+        for j in (0, 131, c - 1):
+            assert (oracle.fft(1, coeffs[j]) == vals[j]).all()
+        wN = lib.p2o_two_adic_generator(1, log_n + r)
+        for row, k in list(zip(rows, ks))[:5]:
+            x = F.generator * pow(wN, lib.p2o_reverse_bits(k, log_n + r), p) % p
+            col = int(rng.integers(0, c))
+            # P(x) with vectorised powers: x^j for j < n by doubling, then a dot product below 2^53
+            pw = np.ones(n, dtype=np.uint64)
+            step, length = x, 1
+            while length < n:
+                pw[length:2 * length] = pw[:length] * np.uint64(step) % np.uint64(p)
+                step = step * step % p
+                length *= 2
+            acc = int(np.sum(coeffs[col].astype(np.uint64) * pw % np.uint64(p), dtype=np.uint64)) % p
+            assert acc == int(row[col])
+    finally:
+        tree.free()
+
+
+def test_three_pass_ntt_plan_at_production_size(ctx, oracle):
+    """2^23 rows is a genuine three-pass transform (8/8/7 tiles): bit-exact against the oracle on a few columns --
+    coefficients, every leaf, every digest, the cap.  (The forced-small-tile test below walks the same code at sizes
+    where every shape can be tried; this one pins the production plan itself.)"""
+    import plonky2_goldibear_b200 as p2g
+    F = fields()[0]
+    log_n, c, r, h = 23, 5, 1, 3
+    vals = synthetic_columns(F.order, F.dtype, c, 1 << log_n, seed=23)
+    batch = p2g.PolynomialBatch.from_values(F, list(vals), r, False, h, ctx=ctx)
+    ref = oracle.commit(0, vals, oracle.VALUES, r, h)
+    assert (np.stack(batch.polynomials) == ref["coeffs"]).all()
+    assert (batch.merkle_tree.leaves == ref["leaves"]).all()
+    assert (batch.merkle_tree.cap.hashes == ref["cap"]).all() and (batch.merkle_tree.digests == ref["digests"]).all()
 
 
 def test_wide_tile_two_pass_ntt_plan(ctx, oracle):
