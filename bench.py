@@ -641,6 +641,22 @@ def run_ours(args, field_name, check_only=False):
                         "h2d_bytes_per_step": int(c * n * es), "d2h_bytes_per_step": int(k_cap.nbytes + q_rows.nbytes + q_sib.nbytes),
                         "note": "P2G_FLAG_KEEP_ON_DEVICE: outputs stay in HBM; cap + 28 queried rows and Merkle paths copied back"}
 
+    # ---- the library's own multi-device context (one process drives all GPUs): rank 0 runs it while the others wait on a
+    # CPU barrier (an NCCL barrier would park a spinning kernel on the very GPUs being measured)
+    lib_multi = None
+    if G > 1 and not args.no_library_multi and not check_only:
+        cpu_group = dist.new_group(backend="gloo")
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                lib_multi = library_multi_bench(args, field_name, G)
+            except SystemExit:
+                raise
+            except Exception as e:
+                lib_multi = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        dist.barrier(group=cpu_group)
+
     if rank != 0:
         if G > 1:
             dist.destroy_process_group()
@@ -697,7 +713,7 @@ def run_ours(args, field_name, check_only=False):
         "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64" if field_name == "gl" else "u32", "data": "synthetic",
         "config": workload_config(args, field_name), "clocks": clocks, "e2e": e2e, "e2e_device_resident_outputs": e2e_resident,
-        "e2e_pageable": e2e_pageable,
+        "e2e_pageable": e2e_pageable, "library_multi_device": lib_multi,
         "gpu_launches": int(launches),
         "roofline": roofline, "roofline_ntt": roofline_ntt, "int_pipe": int_pipe,
         "stage_ms": {"inverse_ntt": ksec[0] * 1e3, "lde_ntt": ksec[1] * 1e3, "leaf_sponge": ksec[2] * 1e3, "tree_levels": ksec[3] * 1e3},
@@ -719,6 +735,114 @@ def run_ours(args, field_name, check_only=False):
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if G > 1:
         dist.destroy_process_group()
+
+
+def library_multi_bench(args, field_name, G):
+    """The same job through the library's own multi-device context (p2g_init(device_ids, G), ONE process): the inverse-NTT
+    exchange, the event barrier and the coset sharding all live behind p2g_commit.  Run by rank 0 after the rank-per-GPU
+    measurement (the other ranks wait on a CPU barrier).  Wall clock around the calls -- p2g_commit returns when every
+    device has finished -- so launch and join overhead are inside the numbers."""
+    import plonky2_goldibear_b200 as p2g
+    from plonky2_goldibear_b200 import _lib
+    from util import synthetic_columns
+    F = p2g.GOLDILOCKS if field_name == "gl" else p2g.BABYBEAR
+    L, c, r, h = args.log_n, args.cols, args.rate_bits, args.cap_height
+    n, N = 1 << L, 1 << (L + r)
+    es, d_el = F.elem_bytes, F.num_hash_out_elts
+    ctx = p2g.Context(list(range(G)))
+    out = {"devices": G, "how": "one process, p2g_init with %d devices; host wall clock around p2g_commit" % G}
+    try:
+        # parity first: 2^12 rows through the multi-device context against the oracle
+        from oracle import p2o
+        fid = p2o.GL if field_name == "gl" else p2o.BB
+        small = synthetic_columns(F.order, F.dtype, c, 1 << min(12, L))
+        ref = p2o.commit(fid, small, p2o.VALUES, r, h, threads=host_cores())
+        b = p2g.PolynomialBatch.from_values(F, list(small), r, False, h, ctx=ctx)
+        ok = ((np.stack(b.polynomials) == ref["coeffs"]).all() and (b.merkle_tree.leaves == ref["leaves"]).all() and
+              (b.merkle_tree.digests == ref["digests"]).all() and (b.merkle_tree.cap.hashes == ref["cap"]).all())
+        if not ok:
+            raise SystemExit("PARITY FAILURE: multi-device context disagrees with the oracle at 2^12 x %d" % c)
+        out["parity"] = "2^%d x %d commit through the multi-device context equals the oracle's (coefficients, leaves, digests, cap)" % (min(12, L), c)
+        del b, ref
+        host_in = ctx.pinned_empty((c, n), F.dtype)
+        for cb in range(0, c, 8):
+            ce = min(cb + 8, c)
+            host_in[cb:ce] = synthetic_columns(F.order, F.dtype, ce - cb, n, col_begin=cb)
+        keep = []
+
+        def ptrs(values):
+            arr = (ctypes.c_void_p * len(values))(*values)
+            keep.append(arr)
+            return ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
+
+        def desc_for(flags):
+            d = _lib.CommitDesc()
+            d.field, d.hash, d.repr, d.input_kind = F.field_id, F.hash_id, 0, 0
+            d.log_n, d.num_cols, d.rate_bits, d.cap_height = L, c, r, h
+            d.flags = flags
+            return d
+
+        cap = np.empty((1 << h, d_el), dtype=F.dtype)
+        handle = ctypes.c_void_p()
+
+        def run(desc, steps, free_batch):
+            times = []
+            for i in range(steps + 2):
+                t0 = time.perf_counter()
+                ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(desc)))
+                times.append(time.perf_counter() - t0)
+                if free_batch:
+                    ctx.lib.p2g_batch_free(ctx.handle, handle)
+            return float(np.mean(times[2:]))
+
+        # (a) inputs already in HBM (each device holds its column slice), outputs stay in HBM: the device-resident step
+        cpr = (c + G - 1) // G
+        dev_ptrs = []
+        for e in range(G):
+            sub = ctx.lib.p2g_sub_context(ctx.handle, e)
+            col0 = min(e * cpr, c)
+            ncol = min(cpr, c - col0)
+            ptr = ctx.lib.p2g_dev_alloc(sub, max(ncol, 1) * n * es)
+            if not ptr:
+                raise RuntimeError("p2g_dev_alloc failed on device %d" % e)
+            if ncol:
+                ctx.check(ctx.lib.p2g_memcpy_async(sub, ptr, host_in[col0].ctypes.data, ncol * n * es, 0))
+            dev_ptrs.append((sub, ptr))
+        d_res = desc_for(_lib.FLAG_DEVICE_INPUT | _lib.FLAG_KEEP_ON_DEVICE)
+        d_res.col_ptrs = ptrs([p_ for _, p_ in dev_ptrs])
+        d_res.cap_out, d_res.batch_out = cap.ctypes.data, ctypes.pointer(handle)
+        t = run(d_res, args.steps, True)
+        out["device_resident"] = {"ms_per_step": t * 1e3, "value": (c << L) / t, "unit": UNIT,
+                                  "note": "column slices resident on their devices in, batch resident out, cap to the host"}
+        cap_res = cap.copy()
+        for sub, ptr in dev_ptrs:
+            ctx.lib.p2g_dev_free(sub, ptr)
+        # (b) pinned host columns in, outputs resident (the form in which more GPUs can beat the host link)
+        d_keep = desc_for(_lib.FLAG_KEEP_ON_DEVICE)
+        d_keep.col_ptrs = ptrs([host_in[j].ctypes.data for j in range(c)])
+        d_keep.cap_out, d_keep.batch_out = cap.ctypes.data, ctypes.pointer(handle)
+        t = run(d_keep, args.e2e_steps, True)
+        assert (cap == cap_res).all()
+        out["e2e_device_resident_outputs"] = {"ms_per_step": t * 1e3, "value": (c << L) / t, "unit": UNIT,
+                                              "h2d_bytes_per_step": int(c * n * es), "d2h_bytes_per_step": int(cap.nbytes)}
+        # (c) the full drop-in: every output back in (pinned) host buffers
+        if not args.no_e2e:
+            h_coeffs = ctx.pinned_empty((c, n), F.dtype)
+            h_leaves = ctx.pinned_empty((N, c), F.dtype)
+            h_digests = ctx.pinned_empty((2 * (N - (1 << h)), d_el), F.dtype)
+            d_all = desc_for(0)
+            d_all.col_ptrs = ptrs([host_in[j].ctypes.data for j in range(c)])
+            d_all.coeffs_out = ptrs([h_coeffs[j].ctypes.data for j in range(c)])
+            d_all.leaves_out, d_all.leaf_pitch = h_leaves.ctypes.data, c
+            d_all.digests_out, d_all.cap_out = h_digests.ctypes.data, cap.ctypes.data
+            t = run(d_all, args.e2e_steps, False)
+            assert (cap == cap_res).all()
+            out["e2e"] = {"ms_per_step": t * 1e3, "value": (c << L) / t, "unit": UNIT, "h2d_bytes_per_step": int(c * n * es),
+                          "d2h_bytes_per_step": int(h_coeffs.nbytes + h_leaves.nbytes + h_digests.nbytes + cap.nbytes)}
+        out["cap0"] = [int(x) for x in cap_res[0]]
+    finally:
+        ctx.close()
+    return out
 
 
 def cpu_baseline(args, field_name):
@@ -852,6 +976,8 @@ def main():
     ap.add_argument("--no-parity-check", action="store_true",
                     help="N > 1: skip the 2^12-row commit through the same exchange that is compared with the oracle before timing")
     ap.add_argument("--no-latency", action="store_true", help="skip the small-shape latency entries (configs 1 and 4)")
+    ap.add_argument("--no-library-multi", action="store_true",
+                    help="N > 1: skip the second pass that runs the job through the library's single-process multi-device context")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: timing rules ask for >= 3 warm-up steps; got %d" % args.warmup)

@@ -58,10 +58,26 @@ enum {
 
 typedef struct p2g_ctx p2g_ctx;
 
-/* Context: one CUDA device, one stream, resident twiddle / round-constant tables, a reusable workspace.
- * device_ids/n_devices: the device this context drives (n_devices must be 1; multi-GPU = one context per
- * device/process, see p2g_commit_desc.shard_*). */
+/* Context.
+ * n_devices == 1: one CUDA device, its streams, resident twiddle / round-constant tables, a reusable workspace.
+ * n_devices in {2, 4, 8}: a MULTI-DEVICE context for one process (a rayon-style prover with a single address space,
+ *   maybe_rayon/src/lib.rs:5-20): one single-device context per entry of device_ids, peer access enabled between every
+ *   pair, and a gather buffer per device.  p2g_commit on it runs the whole job: device d computes the inverse NTT of
+ *   its column slice and stores the coefficients into every device's gather buffer from the transform's epilogue
+ *   (peer stores over NVLink / NVSwitch), an event per device is the cross-device barrier, then device d extends and
+ *   hashes LDE cosets [d * 2^rate_bits / n, ...) and writes its leaf rows, digest slice and cap entries straight into
+ *   the caller's buffers over its own PCIe link.  Requires 2^rate_bits >= n_devices and
+ *   cap_height >= log2(n_devices).  Flags accepted: NO_LEAVES_OUT, KEEP_ON_DEVICE (the batch handle then spans the
+ *   devices; get_rows / prove / download route by leaf index) and DEVICE_INPUT (col_ptrs[d] = device pointer ON DEVICE d
+ *   to that device's column slice, columns [d * ceil(c / n), ...) x n values).  Every other entry point of a
+ *   multi-device context (p2g_merkle, p2g_transform, p2g_permute, p2g_fri_*) is served by its first device.
+ *   The same device id may be listed more than once: its shards then share that GPU (how the partition is tested on a
+ *   one-GPU box).
+ * Multi-PROCESS sharding (one context per GPU and process, exchange by CUDA IPC) stays available through
+ * p2g_commit_desc.shard_* and p2g_intt_allgather. */
 int32_t p2g_init(const int32_t *device_ids, int32_t n_devices, p2g_ctx **out_ctx);
+int32_t p2g_num_devices(p2g_ctx *ctx);
+p2g_ctx *p2g_sub_context(p2g_ctx *ctx, int32_t index); /* the single-device context of device_ids[index] (ctx itself when n = 1) */
 void p2g_destroy(p2g_ctx *ctx);
 const char *p2g_last_error(p2g_ctx *ctx); /* ctx may be NULL: last error of p2g_init on this thread */
 int32_t p2g_abi_version(void);

@@ -54,6 +54,7 @@ EXPORTS = [
     "p2g_batch_download", "p2g_batch_shape", "p2g_batch_free", "p2g_dev_alloc", "p2g_dev_free", "p2g_ipc_export",
     "p2g_ipc_import", "p2g_ipc_close", "p2g_intt_allgather", "p2g_memcpy_async",
     "p2g_fri_begin", "p2g_fri_commit_layer", "p2g_fri_fold", "p2g_fri_finish", "p2g_fri_shape", "p2g_fri_free", "p2g_fri_pow",
+    "p2g_num_devices", "p2g_sub_context",
 ]
 
 
@@ -141,6 +142,10 @@ def load_library() -> ctypes.CDLL:
         lib.p2g_fri_pow.restype = i32
         lib.p2g_fri_free.argtypes = [vp, vp]
         lib.p2g_fri_free.restype = None
+        lib.p2g_num_devices.argtypes = [vp]
+        lib.p2g_num_devices.restype = i32
+        lib.p2g_sub_context.argtypes = [vp, i32]
+        lib.p2g_sub_context.restype = vp
         _LIB = lib
         return lib
 
@@ -148,11 +153,16 @@ def load_library() -> ctypes.CDLL:
 class Context:
     """One GPU context (p2g_init): a stream, resident tables and a reusable device workspace."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: one device index, or a list of 2 / 4 / 8 indices for a multi-device context (one process drives them
+        all; p2g_commit shards the job by LDE coset, include/p2g.h)."""
         self.lib = load_library()
         self.handle = ctypes.c_void_p()
-        dev = (ctypes.c_int32 * 1)(device)
-        rc = self.lib.p2g_init(dev, 1, ctypes.byref(self.handle))
+        devices = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+        self.devices = devices
+        device = devices[0]
+        dev = (ctypes.c_int32 * len(devices))(*devices)
+        rc = self.lib.p2g_init(dev, len(devices), ctypes.byref(self.handle))
         if rc != 0:
             msg = self.lib.p2g_last_error(None)
             raise P2GError(rc, msg.decode() if msg else "p2g_init failed")

@@ -7,12 +7,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -76,6 +78,9 @@ struct p2g_batch {
     uint32_t log_leaves = 0, cap_height = 0;
     uint64_t num_digests = 0, num_cap = 0;
     void *leaves = nullptr, *digests = nullptr, *cap = nullptr, *coeffs = nullptr;
+    // result of a commit on a multi-device context: one device-resident batch per device (coset shard d = leaf rows
+    // [d * rows, (d + 1) * rows), the matching digest slice and cap entries); `rows` etc. above then describe ONE shard
+    std::vector<p2g_batch *> shards;
 };
 
 // State of one FRI commit phase between layers (fri/prover.rs:83-133): the coefficient vector of the current
@@ -117,6 +122,12 @@ struct p2g_ctx {
     // blocks costs ~100 ms and synchronises the device)
     std::vector<Buffer> pool;
     size_t pool_bytes = 0;
+    // multi-device context (p2g_init with n_devices > 1): this object only coordinates; every device has its own
+    // single-device context, a gather buffer that receives all coefficient columns over NVLink, and an event that says
+    // "this device's share of the inverse NTT has been stored everywhere"
+    std::vector<p2g_ctx *> subs;
+    std::vector<Buffer> gather;
+    std::vector<cudaEvent_t> intt_done;
 
     int fail(int code, const char *fmt, ...) {
         char buf[512];
@@ -502,6 +513,254 @@ double ev_seconds(cudaEvent_t a, cudaEvent_t b) {
     return ms * 1e-3;
 }
 
+int32_t init_multi(const int32_t *device_ids, int32_t n_devices, p2g_ctx **out_ctx);
+int32_t commit_multi(p2g_ctx *ctx, p2g_commit_desc *d);
+
+// a call every thread of a multi-device commit makes once: returns when all of them have arrived
+struct ThreadBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    unsigned waiting = 0, generation = 0, parties;
+    explicit ThreadBarrier(unsigned n) : parties(n) {}
+    void arrive_and_wait() {
+        std::unique_lock<std::mutex> lock(mu);
+        unsigned gen = generation;
+        if (++waiting == parties) {
+            waiting = 0;
+            generation++;
+            cv.notify_all();
+        } else {
+            cv.wait(lock, [&] { return gen != generation; });
+        }
+    }
+};
+
+}  // namespace
+
+// ---- multi-device contexts (p2g_init(device_ids, n) holds everything the coset partition needs) ----------
+// One process, one host thread per device for the duration of a call.  Partition: device d runs the inverse
+// NTT of its column slice and stores the coefficients into EVERY device's gather buffer from the transform's epilogue
+// (peer stores over NVLink, run_transform's peer list); an event per device + a host-side rendezvous is the cross-device
+// barrier (each stream then waits on every other device's event: no collective library); then device d extends and
+// hashes its own cosets [d * 2^r / G, ...) and writes leaf rows [d * N / G, ...), the matching digest slice and cap
+// entries straight into the caller's buffers over its own PCIe link.  Nothing else crosses devices.
+namespace {
+
+int32_t init_multi(const int32_t *device_ids, int32_t n_devices, p2g_ctx **out_ctx) {
+    p2g_ctx *ctx = new p2g_ctx();
+    ctx->device = device_ids[0];
+    for (int d = 0; d < n_devices; d++) {
+        p2g_ctx *sub = nullptr;
+        int32_t rc = p2g_init(&device_ids[d], 1, &sub);
+        if (rc != P2G_OK) {
+            for (p2g_ctx *s2 : ctx->subs) p2g_destroy(s2);
+            delete ctx;
+            return rc;  // g_init_error was set by the failing single-device init
+        }
+        ctx->subs.push_back(sub);
+    }
+    // every device stores into every other device's gather buffer (the same device may be listed more than once: its
+    // shards then share it, which is how the partition is exercised on a one-GPU box)
+    for (int a = 0; a < n_devices; a++)
+        for (int b = 0; b < n_devices; b++) {
+            if (device_ids[a] == device_ids[b]) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, device_ids[a], device_ids[b]);
+            if (!can) {
+                g_init_error = "p2g_init: devices " + std::to_string(device_ids[a]) + " and " + std::to_string(device_ids[b]) +
+                               " cannot access each other's memory (no NVLink / PCIe peer path)";
+                for (p2g_ctx *s2 : ctx->subs) p2g_destroy(s2);
+                delete ctx;
+                return P2G_ERR_UNSUPPORTED;
+            }
+            cudaSetDevice(device_ids[a]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                g_init_error = std::string("p2g_init: cudaDeviceEnablePeerAccess failed: ") + cudaGetErrorString(e);
+                for (p2g_ctx *s2 : ctx->subs) p2g_destroy(s2);
+                delete ctx;
+                return P2G_ERR_CUDA;
+            }
+            cudaGetLastError();
+        }
+    ctx->gather.resize(n_devices);
+    ctx->intt_done.resize(n_devices);
+    for (int d = 0; d < n_devices; d++) {
+        cudaSetDevice(device_ids[d]);
+        cudaEventCreateWithFlags(&ctx->intt_done[d], cudaEventDisableTiming);
+    }
+    *out_ctx = ctx;
+    return P2G_OK;
+}
+
+int32_t commit_multi(p2g_ctx *ctx, p2g_commit_desc *d) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const unsigned G = (unsigned)ctx->subs.size(), lg = ilog2(G);
+    const FieldInfo *fp;
+    int rc = check_field_hash(ctx, d->field, d->hash, &fp);
+    if (rc) return rc;
+    const FieldInfo &f = *fp;
+    const int repr = f.id == FIELD_BB ? d->repr : 0;
+    const unsigned allowed = P2G_FLAG_NO_LEAVES_OUT | P2G_FLAG_KEEP_ON_DEVICE | P2G_FLAG_DEVICE_INPUT;
+    if (d->flags & ~allowed)
+        return ctx->fail(P2G_ERR_UNSUPPORTED, "multi-device context: only NO_LEAVES_OUT, KEEP_ON_DEVICE and DEVICE_INPUT "
+                                              "(one column-slice pointer per device) are supported");
+    if (d->shard_count) return ctx->fail(P2G_ERR_INVALID, "multi-device context: the library shards the job itself (shard_count must be 0)");
+    if (d->num_cols == 0) return ctx->fail(P2G_ERR_INVALID, "empty polynomial batch (the reference panics on polynomials[0])");
+    if (!d->col_ptrs) return ctx->fail(P2G_ERR_INVALID, "col_ptrs is NULL");
+    if (d->input_kind != P2G_INPUT_VALUES && d->input_kind != P2G_INPUT_COEFFS) return ctx->fail(P2G_ERR_INVALID, "bad input_kind");
+    const unsigned L = d->log_n, r = d->rate_bits, LN = L + r, h = d->cap_height;
+    if (lg > r) return ctx->fail(P2G_ERR_UNSUPPORTED, "%u devices exceed the 2^rate_bits = %u cosets", G, 1u << r);
+    if (h > LN) return ctx->fail(P2G_ERR_INVALID, "cap_height=%u should be at most log2(leaves.len())=%u", h, LN);
+    if (h < lg)
+        return ctx->fail(P2G_ERR_UNSUPPORTED, "multi-device context: cap_height %u < log2(devices) %u leaves cap entries that span "
+                                              "devices; commit per shard and join with p2g_merkle_finish_cap", h, lg);
+    if (LN > f.two_adicity || LN > 30 || L > 3 * MAX_TILE_LOG) return ctx->fail(P2G_ERR_INVALID, "LDE size 2^%u unsupported", LN);
+    const bool keep = d->flags & P2G_FLAG_KEEP_ON_DEVICE, dev_in = d->flags & P2G_FLAG_DEVICE_INPUT;
+    if (keep && !d->batch_out) return ctx->fail(P2G_ERR_INVALID, "P2G_FLAG_KEEP_ON_DEVICE needs batch_out");
+    const bool values = d->input_kind == P2G_INPUT_VALUES;
+    if (dev_in && !values) return ctx->fail(P2G_ERR_UNSUPPORTED, "multi-device context: DEVICE_INPUT takes values (column slices per device)");
+    const uint64_t n = (uint64_t)1 << L, N = (uint64_t)1 << LN;
+    const unsigned c = d->num_cols, width = c + d->num_salt_cols;
+    const size_t col_bytes = n * f.elem;
+    const unsigned cpr = (c + G - 1) / G;  // columns whose inverse NTT a device owns
+    const uint64_t rows_local = N >> lg, num_cap_local = ((uint64_t)1 << h) >> lg;
+    const uint64_t digests_local = 2 * (rows_local - num_cap_local);
+    const uint64_t out_pitch = d->leaf_pitch ? d->leaf_pitch : width;
+    if (out_pitch < width) return ctx->fail(P2G_ERR_INVALID, "leaf_pitch smaller than the leaf length");
+    if (!dev_in)
+        for (unsigned j = 0; j < c; j++)
+            if (!d->col_ptrs[j]) return ctx->fail(P2G_ERR_INVALID, "col_ptrs[%u] is NULL", j);
+
+    // gather buffers: all coefficient columns on every device (column slot j of device e's buffer = column j)
+    if (values)
+        for (unsigned e = 0; e < G; e++) {
+            p2g_ctx *sub = ctx->subs[e];
+            cudaSetDevice(sub->device);
+            std::lock_guard<std::mutex> sl(sub->mu);
+            int rc2 = ensure(sub, ctx->gather[e], (size_t)G * cpr * col_bytes);
+            if (rc2) return ctx->fail(rc2, "device %d: %s", sub->device, sub->error.c_str());
+        }
+
+    std::vector<p2g_commit_desc> descs(G, *d);
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> errs(G);
+    std::vector<p2g_batch *> shard_batches(G, nullptr);
+    std::vector<const void *> gather_base(G, nullptr);
+    ThreadBarrier barrier(G);
+    auto worker = [&](unsigned e) {
+        p2g_ctx *sub = ctx->subs[e];
+        int &wrc = rcs[e];
+        auto fail_here = [&](int code, const std::string &msg) {
+            wrc = code;
+            errs[e] = "device " + std::to_string(sub->device) + ": " + msg;
+        };
+        if (cudaSetDevice(sub->device) != cudaSuccess) fail_here(P2G_ERR_CUDA, "cudaSetDevice failed");
+        const unsigned col0 = std::min(e * cpr, c), ncol = std::min(cpr, c - col0);
+        if (values && !wrc) {
+            std::lock_guard<std::mutex> sl(sub->mu);
+            cudaStream_t st = sub->stream;
+            cudaError_t ce = cudaSuccess;
+            int rc2 = ncol ? ensure(sub, sub->in, (size_t)ncol * col_bytes) : 0;
+            if (rc2) fail_here(rc2, sub->error);
+            // this device's column slice: up from the host (adjacent columns in one copy), or across from the caller's device buffer
+            if (!wrc && ncol) {
+                if (dev_in) {
+                    ce = cudaMemcpyAsync(sub->in.ptr, d->col_ptrs[e], (size_t)ncol * col_bytes, cudaMemcpyDeviceToDevice, st);
+                } else {
+                    for (unsigned j = col0; j < col0 + ncol && ce == cudaSuccess;) {
+                        unsigned k = j + 1;
+                        while (k < col0 + ncol && (const char *)d->col_ptrs[k] == (const char *)d->col_ptrs[k - 1] + col_bytes) k++;
+                        ce = cudaMemcpyAsync((char *)sub->in.ptr + (size_t)(j - col0) * col_bytes, d->col_ptrs[j], (size_t)(k - j) * col_bytes,
+                                             cudaMemcpyHostToDevice, st);
+                        j = k;
+                    }
+                }
+                if (ce != cudaSuccess) fail_here(P2G_ERR_CUDA, std::string("input copy failed: ") + cudaGetErrorString(ce));
+            }
+            // inverse NTT of the slice, coefficients stored into every device's gather buffer from the last pass' epilogue
+            if (!wrc && ncol) {
+                void *peers[8];
+                unsigned np_ = 0;
+                for (unsigned o = 0; o < G; o++)
+                    if (o != e) peers[np_++] = (char *)ctx->gather[o].ptr + (size_t)col0 * col_bytes;
+                rc2 = run_transform(sub, f, repr, true, L, ncol, sub->in.ptr, nullptr, (char *)ctx->gather[e].ptr + (size_t)col0 * col_bytes, n, 0,
+                                    0, peers, np_);
+                if (rc2) fail_here(rc2, sub->error);
+            }
+            if (cudaEventRecord(ctx->intt_done[e], st) != cudaSuccess && !wrc) fail_here(P2G_ERR_CUDA, "cudaEventRecord failed");
+            // `polynomials` of this slice start their way home on the copy stream while the LDE runs
+            if (!wrc && ncol && d->coeffs_out && !keep) {
+                cudaStreamWaitEvent(sub->copy_stream, ctx->intt_done[e], 0);
+                rc2 = copy_columns_home(sub, d->coeffs_out, col0, col0 + ncol, ctx->gather[e].ptr, col_bytes, sub->copy_stream);
+                if (rc2) fail_here(rc2, sub->error);
+            }
+        }
+        barrier.arrive_and_wait();  // every device's event is recorded (or its failure noted)
+        bool any_failed = false;
+        for (unsigned o = 0; o < G; o++) any_failed |= rcs[o] != 0;
+        if (any_failed) {
+            cudaStreamSynchronize(sub->stream);
+            cudaStreamSynchronize(sub->copy_stream);
+            return;
+        }
+        if (values)
+            for (unsigned o = 0; o < G; o++)
+                if (o != e) cudaStreamWaitEvent(sub->stream, ctx->intt_done[o], 0);  // the cross-device barrier, on the streams
+        // this device's cosets: LDE + tree of shard e, outputs straight into the caller's slices
+        p2g_commit_desc &sd = descs[e];
+        sd.shard_index = e;
+        sd.shard_count = G;
+        sd.flags = d->flags & (P2G_FLAG_NO_LEAVES_OUT | P2G_FLAG_KEEP_ON_DEVICE);
+        if (values) {
+            sd.input_kind = P2G_INPUT_COEFFS;
+            sd.flags |= P2G_FLAG_DEVICE_INPUT;
+            gather_base[e] = ctx->gather[e].ptr;
+            sd.col_ptrs = &gather_base[e];
+            sd.coeffs_out = nullptr;
+        }
+        if (sd.leaves_out) sd.leaves_out = (char *)d->leaves_out + (size_t)e * rows_local * out_pitch * f.elem;
+        if (sd.digests_out) sd.digests_out = (char *)d->digests_out + (size_t)e * digests_local * 32;
+        if (sd.cap_out) sd.cap_out = (char *)d->cap_out + (size_t)e * num_cap_local * 32;
+        sd.leaf_pitch = out_pitch;
+        if (keep) sd.batch_out = &shard_batches[e];
+        int rc3 = p2g_commit(sub, &sd);
+        if (rc3) fail_here(rc3, sub->error);
+        cudaStreamSynchronize(sub->copy_stream);
+    };
+    std::vector<std::thread> threads;
+    for (unsigned e = 1; e < G; e++) threads.emplace_back(worker, e);
+    worker(0);
+    for (auto &t : threads) t.join();
+    cudaSetDevice(ctx->subs[0]->device);
+    for (unsigned e = 0; e < G; e++)
+        if (rcs[e]) {
+            for (unsigned o = 0; o < G; o++)
+                if (shard_batches[o]) p2g_batch_free(ctx->subs[o], shard_batches[o]);
+            ctx->error = errs[e];
+            return rcs[e];
+        }
+    // timings: the slowest device
+    for (int k = 0; k < 4; k++) d->stage_seconds[k] = d->kernel_seconds[k] = 0.0;
+    d->h2d_seconds = d->d2h_seconds = 0.0;
+    for (unsigned e = 0; e < G; e++) {
+        for (int k = 0; k < 4; k++) {
+            d->stage_seconds[k] = std::max(d->stage_seconds[k], descs[e].stage_seconds[k]);
+            d->kernel_seconds[k] = std::max(d->kernel_seconds[k], descs[e].kernel_seconds[k]);
+        }
+        d->h2d_seconds = std::max(d->h2d_seconds, descs[e].h2d_seconds);
+        d->d2h_seconds = std::max(d->d2h_seconds, descs[e].d2h_seconds);
+    }
+    if (keep) {
+        p2g_batch *b = new p2g_batch(*shard_batches[0]);
+        b->leaves = b->digests = b->cap = b->coeffs = nullptr;  // the shards own the memory
+        b->leaves_bytes = b->digests_bytes = b->cap_bytes = b->coeffs_bytes = 0;
+        b->shards = shard_batches;
+        *d->batch_out = b;  // (every shard has already written its cap entries to cap_out)
+    }
+    return P2G_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -511,10 +770,11 @@ int32_t p2g_abi_version(void) { return P2G_ABI_VERSION; }
 int32_t p2g_init(const int32_t *device_ids, int32_t n_devices, p2g_ctx **out_ctx) {
     if (!out_ctx) return P2G_ERR_INVALID;
     *out_ctx = nullptr;
-    if (n_devices != 1 || !device_ids) {
-        g_init_error = "p2g_init: exactly one device per context (use one context per GPU / process)";
+    if (!device_ids || n_devices < 1 || n_devices > 8 || (n_devices & (n_devices - 1))) {
+        g_init_error = "p2g_init: device list of 1, 2, 4 or 8 entries expected";
         return P2G_ERR_INVALID;
     }
+    if (n_devices > 1) return init_multi(device_ids, n_devices, out_ctx);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -559,6 +819,17 @@ int32_t p2g_init(const int32_t *device_ids, int32_t n_devices, p2g_ctx **out_ctx
 
 void p2g_destroy(p2g_ctx *ctx) {
     if (!ctx) return;
+    if (!ctx->subs.empty()) {
+        for (size_t d = 0; d < ctx->subs.size(); d++) {
+            cudaSetDevice(ctx->subs[d]->device);
+            cudaStreamSynchronize(ctx->subs[d]->stream);
+            if (ctx->gather[d].ptr) cudaFree(ctx->gather[d].ptr);
+            cudaEventDestroy(ctx->intt_done[d]);
+        }
+        for (p2g_ctx *sub : ctx->subs) p2g_destroy(sub);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     p2g_release_workspace(ctx);
@@ -576,13 +847,25 @@ void p2g_destroy(p2g_ctx *ctx) {
     delete ctx;
 }
 
-const char *p2g_last_error(p2g_ctx *ctx) { return ctx ? ctx->error.c_str() : g_init_error.c_str(); }
+const char *p2g_last_error(p2g_ctx *ctx) {
+    if (!ctx) return g_init_error.c_str();
+    // entry points a multi-device context hands to its first device leave their message there
+    if (!ctx->subs.empty() && ctx->error.empty()) return ctx->subs[0]->error.c_str();
+    return ctx->error.c_str();
+}
+
+int32_t p2g_num_devices(p2g_ctx *ctx) { return !ctx ? 0 : (ctx->subs.empty() ? 1 : (int32_t)ctx->subs.size()); }
+p2g_ctx *p2g_sub_context(p2g_ctx *ctx, int32_t index) {
+    if (!ctx || index < 0) return nullptr;
+    if (ctx->subs.empty()) return index == 0 ? ctx : nullptr;
+    return (size_t)index < ctx->subs.size() ? ctx->subs[index] : nullptr;
+}
 
 void *p2g_host_alloc(p2g_ctx *ctx, size_t bytes) {
     if (!ctx) return nullptr;
     cudaSetDevice(ctx->device);
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {  // pinned for every device of the process
         cudaGetLastError();
         ctx->fail(P2G_ERR_OOM, "cudaHostAlloc(%zu) failed", bytes);
         return nullptr;
@@ -596,11 +879,24 @@ void p2g_host_free(p2g_ctx *ctx, void *ptr) {
 
 uint64_t p2g_workspace_bytes(p2g_ctx *ctx) {
     if (!ctx) return 0;
+    if (!ctx->subs.empty()) {
+        uint64_t total = 0;
+        for (size_t e = 0; e < ctx->subs.size(); e++) total += p2g_workspace_bytes(ctx->subs[e]) + ctx->gather[e].bytes;
+        return total;
+    }
     return ctx->in.bytes + ctx->coeffs.bytes + ctx->tmp.bytes + ctx->leaves.bytes + ctx->digests.bytes + ctx->cap.bytes +
            ctx->salts.bytes + ctx->misc.bytes + ctx->pass_table_bytes + ctx->pool_bytes;
 }
 void p2g_release_workspace(p2g_ctx *ctx) {
     if (!ctx) return;
+    if (!ctx->subs.empty()) {
+        for (size_t e = 0; e < ctx->subs.size(); e++) {
+            p2g_release_workspace(ctx->subs[e]);
+            if (ctx->gather[e].ptr) cudaFree(ctx->gather[e].ptr);  // (release_workspace left that device current)
+            ctx->gather[e] = Buffer();
+        }
+        return;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     drop_pass_tables(ctx);
@@ -613,12 +909,21 @@ void p2g_release_workspace(p2g_ctx *ctx) {
         b->bytes = 0;
     }
 }
-void *p2g_stream(p2g_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
-uint64_t p2g_kernel_launches(p2g_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *p2g_stream(p2g_ctx *ctx) {
+    if (ctx && !ctx->subs.empty()) ctx = ctx->subs[0];
+    return ctx ? (void *)ctx->stream : nullptr;
+}
+uint64_t p2g_kernel_launches(p2g_ctx *ctx) {
+    if (!ctx) return 0;
+    uint64_t total = ctx->launches;
+    for (p2g_ctx *sub : ctx->subs) total += sub->launches;
+    return total;
+}
 
 int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
     if (!d) return P2G_ERR_INVALID;
+    if (!ctx->subs.empty()) return commit_multi(ctx, d);
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (ctx->pass_table_bytes > ((size_t)2 << 30)) drop_pass_tables(ctx);  // bounded cache; tables are rebuilt on demand
@@ -986,15 +1291,47 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
 
 int32_t p2g_batch_shape(p2g_batch *b, uint64_t *rows, uint64_t *width, uint32_t *num_layers, uint64_t *num_cap) {
     if (!b) return P2G_ERR_INVALID;
-    if (rows) *rows = b->rows;
+    const uint64_t g = b->shards.empty() ? 1 : b->shards.size();  // a multi-device batch: g shards of b->rows rows each
+    if (rows) *rows = b->rows * g;
     if (width) *width = b->width;
     if (num_layers) *num_layers = b->log_leaves - b->cap_height;
-    if (num_cap) *num_cap = b->num_cap;
+    if (num_cap) *num_cap = b->num_cap * g;
+    return P2G_OK;
+}
+
+// multi-device batch: leaf index -> (shard, local index); the shards' trees are the cap subtrees of the whole tree
+// (cap_height >= log2(devices)), so a Merkle path never leaves its shard
+static int32_t batch_route(p2g_ctx *ctx, p2g_batch *b, const uint64_t *idx, uint64_t count, size_t out_stride, void *out, bool prove) {
+    if (ctx->subs.size() != b->shards.size()) return ctx->fail(P2G_ERR_INVALID, "batch does not belong to this context");
+    const uint64_t g = b->shards.size();
+    std::vector<std::vector<uint64_t>> local(g), where(g);
+    for (uint64_t i = 0; i < count; i++) {
+        if (idx[i] >= b->rows * g) return ctx->fail(P2G_ERR_INVALID, "index %llu out of range", (unsigned long long)idx[i]);
+        const uint64_t s_ = idx[i] / b->rows;
+        local[s_].push_back(idx[i] - s_ * b->rows);
+        where[s_].push_back(i);
+    }
+    std::vector<unsigned char> tmp;
+    for (uint64_t s_ = 0; s_ < g; s_++) {
+        if (local[s_].empty()) continue;
+        tmp.resize(local[s_].size() * out_stride);
+        int32_t rc = prove ? p2g_batch_prove(ctx->subs[s_], b->shards[s_], local[s_].data(), local[s_].size(), tmp.data())
+                           : p2g_batch_get_rows(ctx->subs[s_], b->shards[s_], local[s_].data(), local[s_].size(), tmp.data());
+        if (rc) return ctx->fail(rc, "device %d: %s", ctx->subs[s_]->device, ctx->subs[s_]->error.c_str());
+        for (size_t k = 0; k < where[s_].size(); k++)
+            memcpy((char *)out + where[s_][k] * out_stride, tmp.data() + k * out_stride, out_stride);
+    }
     return P2G_OK;
 }
 
 void p2g_batch_free(p2g_ctx *ctx, p2g_batch *b) {
     if (!b) return;
+    if (!b->shards.empty()) {
+        for (size_t s_ = 0; s_ < b->shards.size(); s_++)
+            p2g_batch_free(ctx && s_ < ctx->subs.size() ? ctx->subs[s_] : nullptr, b->shards[s_]);
+        delete b;
+        return;
+    }
     if (ctx) {
         std::lock_guard<std::mutex> lock(ctx->mu);
         cudaSetDevice(ctx->device);
@@ -1014,6 +1351,7 @@ int32_t p2g_batch_get_rows(p2g_ctx *ctx, p2g_batch *b, const uint64_t *row_indic
     if (!ctx) return P2G_ERR_NO_DEVICE;
     if (!b || (count && (!row_indices || !rows_out))) return P2G_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!b->shards.empty()) return batch_route(ctx, b, row_indices, count, (size_t)b->width * b->elem, rows_out, false);
     CK(cudaSetDevice(ctx->device));
     if (!count) return P2G_OK;
     for (uint64_t i = 0; i < count; i++)
@@ -1036,6 +1374,11 @@ int32_t p2g_batch_prove(p2g_ctx *ctx, p2g_batch *b, const uint64_t *leaf_indices
     if (!ctx) return P2G_ERR_NO_DEVICE;
     if (!b || (count && !leaf_indices)) return P2G_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!b->shards.empty()) {
+        if (!count || b->log_leaves == b->cap_height) return P2G_OK;
+        if (!siblings_out) return P2G_ERR_INVALID;
+        return batch_route(ctx, b, leaf_indices, count, (size_t)(b->log_leaves - b->cap_height) * 32, siblings_out, true);
+    }
     CK(cudaSetDevice(ctx->device));
     const uint32_t layers = b->log_leaves - b->cap_height;
     if (!count || !layers) return P2G_OK;
@@ -1060,6 +1403,17 @@ int32_t p2g_batch_download(p2g_ctx *ctx, p2g_batch *b, int32_t what, void *out) 
     if (!ctx) return P2G_ERR_NO_DEVICE;
     if (!b || !out) return P2G_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!b->shards.empty()) {
+        // leaves / digests / cap: the shards' arrays one after the other ARE the whole arrays; coefficients: any shard has all
+        if (ctx->subs.size() != b->shards.size()) return ctx->fail(P2G_ERR_INVALID, "batch does not belong to this context");
+        const size_t per = what == 0 ? (size_t)b->rows * b->width * b->elem : (what == 1 ? (size_t)b->num_digests * 32 : (size_t)b->num_cap * 32);
+        for (size_t s_ = 0; s_ < b->shards.size(); s_++) {
+            if (what == 3 && s_) break;
+            int32_t rc = p2g_batch_download(ctx->subs[s_], b->shards[s_], what, (char *)out + (what == 3 ? 0 : s_ * per));
+            if (rc) return ctx->fail(rc, "device %d: %s", ctx->subs[s_]->device, ctx->subs[s_]->error.c_str());
+        }
+        return P2G_OK;
+    }
     CK(cudaSetDevice(ctx->device));
     const void *src;
     size_t bytes;
@@ -1124,6 +1478,11 @@ static int32_t merkle_locked(p2g_ctx *ctx, p2g_merkle_desc *d) {
 }
 
 int32_t p2g_merkle(p2g_ctx *ctx, p2g_merkle_desc *d) {
+    if (ctx && !ctx->subs.empty()) {
+        int32_t rc_ = p2g_merkle(ctx->subs[0], d);
+        if (rc_) ctx->error = ctx->subs[0]->error;
+        return rc_;
+    }
     if (!ctx) return P2G_ERR_NO_DEVICE;
     if (!d) return P2G_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
@@ -1133,6 +1492,7 @@ int32_t p2g_merkle(p2g_ctx *ctx, p2g_merkle_desc *d) {
 int32_t p2g_merkle_finish_cap(p2g_ctx *ctx, int32_t field, int32_t hash, int32_t repr, const void *roots,
                               uint32_t shard_count, uint32_t cap_height, void *top_digests_out, void *cap_out) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];  // multi-device context: its first device serves this call
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     const FieldInfo *fp;
@@ -1164,6 +1524,7 @@ static unsigned ext_degree(const FieldInfo &f) { return f.id == FIELD_GL ? 2 : 4
 int32_t p2g_fri_begin(p2g_ctx *ctx, int32_t field, int32_t hash, int32_t repr_in, uint32_t degree, uint32_t log_n,
                       const void *coeffs, const void *values, uint32_t flags, p2g_fri **out) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];  // multi-device context: its first device serves this call
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (!out) return ctx->fail(P2G_ERR_INVALID, "out is NULL");
@@ -1237,6 +1598,7 @@ int32_t p2g_fri_begin(p2g_ctx *ctx, int32_t field, int32_t hash, int32_t repr_in
 int32_t p2g_fri_commit_layer(p2g_ctx *ctx, p2g_fri *s, uint32_t arity_bits, uint32_t cap_height, void *cap_out,
                              p2g_batch **tree_out) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];  // multi-device context: its first device serves this call
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (!s || !tree_out) return ctx->fail(P2G_ERR_INVALID, "state / tree_out is NULL");
@@ -1290,6 +1652,7 @@ int32_t p2g_fri_commit_layer(p2g_ctx *ctx, p2g_fri *s, uint32_t arity_bits, uint
 
 int32_t p2g_fri_fold(p2g_ctx *ctx, p2g_fri *s, const void *beta) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];  // multi-device context: its first device serves this call
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (!s || !beta) return ctx->fail(P2G_ERR_INVALID, "state / beta is NULL");
@@ -1352,6 +1715,7 @@ int32_t p2g_fri_fold(p2g_ctx *ctx, p2g_fri *s, const void *beta) {
 
 int32_t p2g_fri_finish(p2g_ctx *ctx, p2g_fri *s, uint32_t rate_bits, void *final_coeffs_out, uint64_t *count_out) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];  // multi-device context: its first device serves this call
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (!s) return ctx->fail(P2G_ERR_INVALID, "state is NULL");
@@ -1381,6 +1745,7 @@ int32_t p2g_fri_shape(p2g_fri *s, uint32_t *log_n, uint64_t *shift) {
 
 void p2g_fri_free(p2g_ctx *ctx, p2g_fri *s) {
     if (!ctx || !s) return;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];
     std::lock_guard<std::mutex> lock(ctx->mu);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -1393,6 +1758,7 @@ void p2g_fri_free(p2g_ctx *ctx, p2g_fri *s) {
 int32_t p2g_fri_pow(p2g_ctx *ctx, int32_t field, int32_t hash, const void *sponge_state, const void *input_buffer,
                     uint32_t input_len, uint32_t min_leading_zeros, uint64_t *witness_out) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];  // multi-device context: its first device serves this call
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     const FieldInfo *fp;
@@ -1433,6 +1799,11 @@ int32_t p2g_fri_pow(p2g_ctx *ctx, int32_t field, int32_t hash, const void *spong
 }
 
 int32_t p2g_permute(p2g_ctx *ctx, int32_t hash, int32_t repr, void *states, uint64_t count) {
+    if (ctx && !ctx->subs.empty()) {
+        int32_t rc_ = p2g_permute(ctx->subs[0], hash, repr, states, count);
+        if (rc_) ctx->error = ctx->subs[0]->error;
+        return rc_;
+    }
     if (!ctx) return P2G_ERR_NO_DEVICE;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
@@ -1452,6 +1823,11 @@ int32_t p2g_permute(p2g_ctx *ctx, int32_t hash, int32_t repr, void *states, uint
 
 int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, uint32_t log_n, uint32_t num_cols,
                       uint32_t rate_bits, uint32_t flags, const void *in, void *out) {
+    if (ctx && !ctx->subs.empty()) {
+        int32_t rc_ = p2g_transform(ctx->subs[0], field, repr, kind, log_n, num_cols, rate_bits, flags, in, out);
+        if (rc_) ctx->error = ctx->subs[0]->error;
+        return rc_;
+    }
     if (!ctx) return P2G_ERR_NO_DEVICE;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
@@ -1514,6 +1890,7 @@ int32_t p2g_transform(p2g_ctx *ctx, int32_t field, int32_t repr, int32_t kind, u
 // ---- multi-GPU plumbing: device buffers that other processes can map, and the fused inverse-NTT + all-gather --------
 void *p2g_dev_alloc(p2g_ctx *ctx, size_t bytes) {
     if (!ctx) return nullptr;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];
     cudaSetDevice(ctx->device);
     void *p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) {
@@ -1524,6 +1901,7 @@ void *p2g_dev_alloc(p2g_ctx *ctx, size_t bytes) {
     return p;
 }
 void p2g_dev_free(p2g_ctx *ctx, void *ptr) {
+    if (ctx && !ctx->subs.empty()) ctx = ctx->subs[0];
     if (ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
@@ -1532,6 +1910,7 @@ void p2g_dev_free(p2g_ctx *ctx, void *ptr) {
 }
 int32_t p2g_ipc_export(p2g_ctx *ctx, void *dev_ptr, uint8_t handle_out[64]) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];  // multi-device context: its first device serves this call
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     CK(cudaSetDevice(ctx->device));
     cudaIpcMemHandle_t h;
@@ -1541,6 +1920,7 @@ int32_t p2g_ipc_export(p2g_ctx *ctx, void *dev_ptr, uint8_t handle_out[64]) {
 }
 int32_t p2g_ipc_import(p2g_ctx *ctx, const uint8_t handle[64], void **dev_ptr_out) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];  // multi-device context: its first device serves this call
     CK(cudaSetDevice(ctx->device));
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
@@ -1549,6 +1929,7 @@ int32_t p2g_ipc_import(p2g_ctx *ctx, const uint8_t handle[64], void **dev_ptr_ou
 }
 int32_t p2g_ipc_close(p2g_ctx *ctx, void *dev_ptr) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];  // multi-device context: its first device serves this call
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaIpcCloseMemHandle(dev_ptr));
@@ -1557,6 +1938,7 @@ int32_t p2g_ipc_close(p2g_ctx *ctx, void *dev_ptr) {
 
 int32_t p2g_memcpy_async(p2g_ctx *ctx, void *dst, const void *src, size_t bytes, int32_t kind) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];  // multi-device context: its first device serves this call
     CK(cudaSetDevice(ctx->device));
     cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
     CK(cudaMemcpyAsync(dst, src, bytes, k, ctx->stream));
@@ -1566,6 +1948,7 @@ int32_t p2g_memcpy_async(p2g_ctx *ctx, void *dst, const void *src, size_t bytes,
 int32_t p2g_intt_allgather(p2g_ctx *ctx, int32_t field, int32_t repr, uint32_t log_n, uint32_t num_cols, uint32_t col_offset,
                            const void *values_dev, void *const *gather_bufs, uint32_t num_bufs) {
     if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];  // multi-device context: its first device serves this call
     std::lock_guard<std::mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (field != P2G_FIELD_GOLDILOCKS && field != P2G_FIELD_BABYBEAR) return ctx->fail(P2G_ERR_UNSUPPORTED, "unknown field");

@@ -662,3 +662,78 @@ def test_device_input_with_host_salts(ctx, oracle, field, log_n, c):
         ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(d)))
         assert (leaves == ref["leaves"]).all() and (digests == ref["digests"]).all() and (cap == ref["cap"]).all()
         assert (coeffs == ref["coeffs"]).all()
+
+
+# ---- multi-device context: one process, p2g_init(device_ids, n), the library shards the commit -------
+def _device_lists():
+    import torch
+    n = torch.cuda.device_count()
+    lists = [[0, 0], [0, 0, 0, 0]]  # the partition on one GPU: the shards share it
+    for g in (2, 4, 8):
+        if n >= g:
+            lists.append(list(range(g)))
+    return lists
+
+
+@pytest.mark.parametrize("field,log_n,c,r,h,kind", [(0, 12, 135, 3, 4, "values"), (1, 11, 70, 3, 3, "values"),
+                                                    (0, 11, 9, 3, 4, "coeffs"), (0, 13, 3, 2, 2, "values")])
+def test_multi_device_context_commit_matches_oracle(oracle, field, log_n, c, r, h, kind):
+    """p2g_commit on a multi-device context: host columns in, the whole job's coefficients / leaves / digests / cap out,
+    bit-exact against the oracle -- the column-sharded inverse NTT with the all-gather fused into its epilogue (peer
+    stores), the event barrier, the coset-sharded LDE + trees writing their slices of the caller's buffers.  On real
+    multi-GPU boxes the device lists [0..g) run over NVLink; [0, 0] and [0, 0, 0, 0] run the same code on one GPU."""
+    import plonky2_goldibear_b200 as p2g
+    F = fields()[field]
+    n = 1 << log_n
+    vals = synthetic_columns(F.order, F.dtype, c, n, seed=51)
+    okind = oracle.VALUES if kind == "values" else oracle.COEFFS
+    ref = oracle.commit(field, vals, okind, r, h)
+    for devs in _device_lists():
+        if len(devs) > (1 << r) or (1 << h) < len(devs):
+            continue
+        mctx = p2g.Context(devs)
+        try:
+            assert mctx.lib.p2g_num_devices(mctx.handle) == len(devs)
+            fn = p2g.PolynomialBatch.from_values if kind == "values" else p2g.PolynomialBatch.from_coeffs
+            for rep in range(2):  # the context is reused: gather buffers and events must be clean for the next call
+                b = fn(F, list(vals), r, False, h, ctx=mctx, pinned_out=bool(rep))
+                if kind == "values":
+                    assert (np.stack(b.polynomials) == ref["coeffs"]).all(), devs
+                assert (b.merkle_tree.leaves == ref["leaves"]).all(), devs
+                assert (b.merkle_tree.digests == ref["digests"]).all(), devs
+                assert (b.merkle_tree.cap.hashes == ref["cap"]).all(), devs
+            # device-resident variant: the batch spans the devices, accessors route by leaf index
+            kb = fn(F, list(vals), r, False, h, ctx=mctx, keep_on_device=True)
+            tree = kb.merkle_tree
+            N = n << r
+            ks = [0, N - 1, N // len(devs), N // len(devs) - 1, 12345 % N]
+            rows = tree.get_many(ks)
+            sibs = tree.prove_many(ks)
+            assert (tree.cap.hashes == ref["cap"]).all()
+            for row, sib, k in zip(rows, sibs, ks):
+                assert (row == ref["leaves"][k]).all()
+                assert oracle.verify_merkle_proof_to_cap(field, row, k, ref["cap"], sib)
+            assert (tree.download("digests") == ref["digests"]).all() and (tree.download("leaves") == ref["leaves"]).all()
+            if kind == "values":
+                assert (kb.download_polynomials() == ref["coeffs"]).all()
+            tree.free()
+        finally:
+            mctx.close()
+
+
+def test_multi_device_context_rejects_what_it_cannot_shard(oracle):
+    import plonky2_goldibear_b200 as p2g
+    F = fields()[0]
+    vals = synthetic_columns(F.order, F.dtype, 3, 1 << 6, seed=1)
+    mctx = p2g.Context([0, 0, 0, 0])
+    try:
+        with pytest.raises(p2g.P2GError) as e:  # cap entries would span devices
+            p2g.PolynomialBatch.from_values(F, list(vals), 3, False, 1, ctx=mctx)
+        assert e.value.code == -5
+        with pytest.raises(p2g.P2GError) as e:  # more devices than cosets
+            p2g.PolynomialBatch.from_values(F, list(vals), 1, False, 4, ctx=mctx)
+        assert e.value.code == -5
+    finally:
+        mctx.close()
+    with pytest.raises(p2g.P2GError):
+        p2g.Context([0, 0, 0])  # 1, 2, 4 or 8 devices
