@@ -140,8 +140,31 @@ __device__ __forceinline__ void cp_async_elem(void *smem, const void *gmem) {
 // (conflict-free) and reads 32-byte pieces of 8 (Goldilocks) / 8-byte pieces of 16 (BabyBear) runs.  Element-sized
 // LDGSTS: no registers, the whole tile is in flight at once.
 template <class E, class BaseOf>
-__device__ __forceinline__ void load_transposed(E *x, u32 lp, u32 lw, u32 live_w, const BaseOf &base_of) {
+__device__ __forceinline__ void load_transposed(E *x, u32 lp, u32 lw, u32 live_w, bool aligned16, const BaseOf &base_of) {
     const u32 W = 1u << lw;
+    if (sizeof(E) == 4 && aligned16 && lp >= 2) {
+        // 4-byte elements: an element-sized LDGSTS touches 16 sectors for 8 useful bytes each (the BabyBear final
+        // passes spent 70% of their shared-memory wavefronts there).  16-byte vector loads instead (4 consecutive
+        // points of one column, whole sectors), scattered to their 4 tile rows from registers.
+        const u32 w = threadIdx.x & (W - 1);
+        const u32 q0 = threadIdx.x >> lw, qstep = blockDim.x >> lw;
+        const u32 nq = (1u << lp) >> 2;
+        if (w < live_w) {
+            const uint4 *g = reinterpret_cast<const uint4 *>(base_of(w));
+#pragma unroll 4
+            for (u32 q = q0; q < nq; q += qstep) {
+                const uint4 v = __ldg(g + q);
+                E *sm = x + ((size_t)(4 * q) << lw) + w;
+                sm[0] = (E)v.x;
+                sm[(size_t)1 << lw] = (E)v.y;
+                sm[(size_t)2 << lw] = (E)v.z;
+                sm[(size_t)3 << lw] = (E)v.w;
+            }
+        } else {
+            for (u32 i = q0; i < (1u << lp); i += qstep) x[((size_t)i << lw) + w] = (E)0;
+        }
+        return;
+    }
     const u32 w = threadIdx.x & (W - 1);
     const u32 i0 = threadIdx.x >> lw, istep = blockDim.x >> lw;
     const u32 np = 1u << lp;
@@ -204,7 +227,7 @@ __global__ void __launch_bounds__(256, F::MIN_CTAS) ntt_final_natural_kernel(con
     E *x = reinterpret_cast<E *>(smem_raw);
     const NaturalTile<F, DIR> t(p, blockIdx.x);
     E *roots_s = x + t.tile_elems();
-    load_transposed<E>(x, t.lp, t.lw, 1u << t.lw, [&](u32 w) { return t.chunk(w); });
+    load_transposed<E>(x, t.lp, t.lw, 1u << t.lw, p.async_ok != 0, [&](u32 w) { return t.chunk(w); });
     const E *roots = stage_roots<F>(p, roots_s, t.lp);
     cp_async_wait_all();
     __syncthreads();
@@ -218,7 +241,7 @@ __global__ void __launch_bounds__(256, F::MIN_CTAS) ntt_final_leaves_kernel(cons
     E *x = reinterpret_cast<E *>(smem_raw);
     const LeavesTile<F, DIR> t(p, blockIdx.x);
     E *roots_s = x + t.tile_elems();
-    load_transposed<E>(x, t.lp, t.lw, t.ncols, [&](u32 w) { return t.src + (size_t)w * t.src_col_stride; });
+    load_transposed<E>(x, t.lp, t.lw, t.ncols, p.async_ok != 0, [&](u32 w) { return t.src + (size_t)w * t.src_col_stride; });
     const E *roots = stage_roots<F>(p, roots_s, t.lp);
     cp_async_wait_all();
     __syncthreads();

@@ -82,3 +82,38 @@ def test_flag_constants_match_header():
     rust = open(os.path.join(ROOT, "integration", "rust", "p2g_sys.rs")).read()
     for name, value in flags.items():
         assert re.search(r"pub const P2G_%s: u32 = %s;" % (name, value), rust), "p2g_sys.rs lacks P2G_" + name
+
+
+def test_rust_bindings_are_generated_from_the_header():
+    """integration/rust/p2g_sys.rs is what tools/gen_rust_bindings.py makes of include/p2g.h today: every exported symbol
+    declared, both #[repr(C)] structs with the header's field order, every constant."""
+    res = subprocess.run(["python", os.path.join(ROOT, "tools", "gen_rust_bindings.py"), "--check"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    rust = open(os.path.join(ROOT, "integration", "rust", "p2g_sys.rs")).read()
+    for name in _declared_symbols():
+        assert re.search(r"pub fn %s\(" % name, rust), "p2g_sys.rs lacks " + name
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "p2g.h")).read(), flags=re.S)
+    bodies = {name: body for body, name in re.findall(r"typedef struct \{([^}]*)\}\s*(p2g_[a-z_]+);", hdr)}
+    for struct in ("p2g_commit_desc", "p2g_merkle_desc"):
+        c_fields = []
+        for stmt in bodies[struct].split(";"):
+            for decl in stmt.split(","):
+                ids = re.findall(r"[A-Za-z_][A-Za-z0-9_]*", re.sub(r"\[\d+\]", "", decl))
+                if ids:
+                    c_fields.append(ids[-1])  # the declarator's name is its last identifier
+        r_body = re.search(r"pub struct %s \{(.*?)\n\}" % struct, rust, flags=re.S).group(1)
+        r_fields = ["repr" if f == "repr_" else f for f in re.findall(r"pub ([a-z_0-9]+):", r_body)]
+        assert r_fields == c_fields, (struct, r_fields, c_fields)
+
+
+def test_rust_shim_has_no_elided_bodies():
+    """cuda_shim.rs and dump_vectors.rs are complete files (not compiled here, but nothing is left to the reader)."""
+    for name in ("cuda_shim.rs", "dump_vectors.rs"):
+        text = open(os.path.join(ROOT, "integration", "rust", name)).read()
+        code = "\n".join(ln.split("//")[0] for ln in text.splitlines())
+        assert "/*" not in code and "todo!" not in code and "unimplemented!" not in code and " .. }" not in code, name
+        assert code.count("{") == code.count("}") and code.count("(") == code.count(")"), name
+    shim = open(os.path.join(ROOT, "integration", "rust", "cuda_shim.rs")).read()
+    for needle in ("pub fn from_values(", "pub fn from_coeffs(", "pub fn new(leaves: Vec<Vec<F>>, cap_height: usize)",
+                   "p2g_commit(ctx, &mut desc)", "p2g_merkle(ctx, &mut desc)", "Polynomial degrees inconsistent"):
+        assert needle in shim, needle

@@ -209,3 +209,31 @@ def test_decimation_in_time_lde_model_matches_the_leaf_order(field, log_n, lps):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import ct_lde_model
     assert ct_lde_model.check(field, log_n, lps)
+
+
+def test_external_vectors_if_present(oracle):
+    """tests/golden/external_vectors.json is the output of integration/rust/dump_vectors.rs, run against the reference's
+    own crates wherever cargo exists.  It does not exist yet (no Rust toolchain in this image: SURVEY 8c); when someone
+    drops it in, this test pins every constant the survey lists as unpinned -- generators, two-adic roots, the extension
+    constant W, one Poseidon2-BabyBear permutation and one from_values cap per field -- on bytes the reference produced."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "external_vectors.json")
+    if not os.path.exists(path):
+        pytest.skip("no external vectors yet (run integration/rust/dump_vectors.rs where cargo exists)")
+    ext = json.load(open(path))
+    lib = oracle.load()
+    for name, fid, adicity in (("goldilocks", oracle.GL, 32), ("babybear", oracle.BB, 27)):
+        e = ext[name]
+        assert lib.p2o_generator(fid) == e["generator"]
+        assert [lib.p2o_two_adic_generator(fid, k) for k in range(adicity + 1)] == e["two_adic_generators"]
+        assert lib.p2o_ext_degree(fid) == e["extension_degree"] and lib.p2o_ext_w(fid) == e["extension_w"]
+        fv = e["from_values"]
+        from util import synthetic_columns
+        vals = synthetic_columns(oracle.ORDER[fid], oracle.DTYPE[fid], fv["cols"], 1 << fv["log_n"], seed=fv["seed"])
+        ref = oracle.commit(fid, vals, oracle.VALUES, fv["rate_bits"], fv["cap_height"])
+        assert ref["cap"].tolist() == fv["cap"]
+    assert oracle.permute(oracle.GL, np.arange(12, dtype=np.uint64)).tolist() == ext["goldilocks"]["poseidon_0_to_11"]
+    assert oracle.permute(oracle.BB, np.arange(16, dtype=np.uint32)).tolist() == ext["babybear"]["poseidon2_0_to_15"]
+    syn = ext["babybear"]["poseidon2_synthetic"]
+    assert oracle.permute(oracle.BB, np.array(syn["input"], dtype=np.uint32)).tolist() == syn["output"]
