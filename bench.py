@@ -885,7 +885,9 @@ def latency_entries(field_name, ctx, p2g):
     else:
         shapes = [(12, 46), (12, 167), (12, 36), (12, 48)]  # narrow BabyBear recursion config
     out = {"how": "host wall clock around PolynomialBatch.from_values / MerkleTree.new, pageable host arrays in and out, "
-                  "rate_bits 3, cap_height 4, median of 30 calls after 5 warm-up calls", "commit_ms": {}, "merkle_ms": {}}
+                  "rate_bits 3, cap_height 4, median of 30 calls after 5 warm-up calls; commit_pinned_reused_ms: the same call with pinned "
+                  "input and output buffers allocated once", "commit_ms": {}, "commit_pinned_reused_ms": {}, "merkle_ms": {}}
+    reuse = {}
     for log_n, c in shapes:
         cols = [rng.integers(0, f.order, size=1 << log_n, dtype=np.uint64).astype(f.dtype) for _ in range(c)]
         ts = []
@@ -894,6 +896,17 @@ def latency_entries(field_name, ctx, p2g):
             p2g.PolynomialBatch.from_values(f, cols, 3, False, 4, ctx=ctx)
             ts.append(time.perf_counter() - t0)
         out["commit_ms"]["2^%d x %d" % (log_n, c)] = float(np.median(ts[5:])) * 1e3
+        # the library call alone: pinned buffers allocated once and reused (no host allocation or page faults inside the
+        # timed call -- a 2^12 x 135 commit returns 35 MB of leaves, which a fresh allocation above glibc's 32 MB mmap
+        # threshold pays for with ~9000 page faults per call)
+        pin = ctx.pinned_empty((c, 1 << log_n), f.dtype)
+        pin[...] = np.stack(cols)
+        ts = []
+        for it in range(35):
+            t0 = time.perf_counter()
+            p2g.PolynomialBatch.from_values(f, list(pin), 3, False, 4, ctx=ctx, pinned_out=True, _reuse=reuse)
+            ts.append(time.perf_counter() - t0)
+        out["commit_pinned_reused_ms"]["2^%d x %d" % (log_n, c)] = float(np.median(ts[5:])) * 1e3
     d = f.extension_degree
     for log_leaves, leaf_len in ((11, 16 * d), (7, 16 * d)):  # arity-16 layers of a 2^15 codeword (fri/prover.rs:104-108)
         leaves = rng.integers(0, f.order, size=(1 << log_leaves, leaf_len), dtype=np.uint64).astype(f.dtype)

@@ -142,29 +142,8 @@ __device__ __forceinline__ void cp_async_elem(void *smem, const void *gmem) {
 template <class E, class BaseOf>
 __device__ __forceinline__ void load_transposed(E *x, u32 lp, u32 lw, u32 live_w, bool aligned16, const BaseOf &base_of) {
     const u32 W = 1u << lw;
-    if (sizeof(E) == 4 && aligned16 && lp >= 2) {
-        // 4-byte elements: an element-sized LDGSTS touches 16 sectors for 8 useful bytes each (the BabyBear final
-        // passes spent 70% of their shared-memory wavefronts there).  16-byte vector loads instead (4 consecutive
-        // points of one column, whole sectors), scattered to their 4 tile rows from registers.
-        const u32 w = threadIdx.x & (W - 1);
-        const u32 q0 = threadIdx.x >> lw, qstep = blockDim.x >> lw;
-        const u32 nq = (1u << lp) >> 2;
-        if (w < live_w) {
-            const uint4 *g = reinterpret_cast<const uint4 *>(base_of(w));
-#pragma unroll 4
-            for (u32 q = q0; q < nq; q += qstep) {
-                const uint4 v = __ldg(g + q);
-                E *sm = x + ((size_t)(4 * q) << lw) + w;
-                sm[0] = (E)v.x;
-                sm[(size_t)1 << lw] = (E)v.y;
-                sm[(size_t)2 << lw] = (E)v.z;
-                sm[(size_t)3 << lw] = (E)v.w;
-            }
-        } else {
-            for (u32 i = q0; i < (1u << lp); i += qstep) x[((size_t)i << lw) + w] = (E)0;
-        }
-        return;
-    }
+    (void)aligned16;  // (16-byte vector loads scattered from registers were measured for the 4-byte field: LDE of 2^22 x 256
+    // 82.9 against 81.7 ms -- fewer shared-memory wavefronts, but the loads then wait in registers instead of in flight)
     const u32 w = threadIdx.x & (W - 1);
     const u32 i0 = threadIdx.x >> lw, istep = blockDim.x >> lw;
     const u32 np = 1u << lp;

@@ -77,7 +77,7 @@ class PolynomialBatch:
     def _commit(cls, field, columns, input_kind, rate_bits, blinding, cap_height, timing, ctx=None,
                 repr: int = REPR_CANONICAL, salts: Optional[Sequence[np.ndarray]] = None, rng=None,
                 shard_index: int = 0, shard_count: int = 0, want_leaves: bool = True, pinned_out: bool = False,
-                keep_on_device: bool = False, leaf_pitch: int = 0):
+                keep_on_device: bool = False, leaf_pitch: int = 0, _reuse: Optional[dict] = None):
         ctx = ctx or _lib.default_context()
         if len(columns) == 0:
             raise IndexError("index out of bounds: the len is 0 but the index is 0")  # polynomials[0], oracle.rs:101
@@ -105,6 +105,17 @@ class PolynomialBatch:
         cap_local = max(cap_height - lg, 0)
         d = field.num_hash_out_elts
         alloc = ctx.pinned_empty if pinned_out else (lambda shape, dtype: np.empty(shape, dtype=dtype))
+        if _reuse is not None:
+            # output buffers handed back by an earlier call of the same shape (latency measurements: pinned allocations
+            # are expensive and never freed before the context closes)
+            base_alloc = alloc
+
+            def alloc(shape, dtype, _n=[0]):
+                key = (_n[0], tuple(shape), np.dtype(dtype).str)
+                _n[0] += 1
+                if key not in _reuse:
+                    _reuse[key] = base_alloc(shape, dtype)
+                return _reuse[key]
         if keep_on_device:
             want_leaves = False
         pitch = leaf_pitch or width
