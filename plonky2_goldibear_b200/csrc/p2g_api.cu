@@ -122,6 +122,9 @@ struct p2g_ctx {
     // blocks costs ~100 ms and synchronises the device)
     std::vector<Buffer> pool;
     size_t pool_bytes = 0;
+    // pinned staging ring for large copies from / to PAGEABLE host memory (two slots, see staged_copy)
+    void *stage_ring = nullptr;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     // multi-device context (p2g_init with n_devices > 1): this object only coordinates; every device has its own
     // single-device context, a gather buffer that receives all coefficient columns over NVLink, and an event that says
     // "this device's share of the inverse NTT has been stored everywhere"
@@ -491,6 +494,112 @@ unsigned ilog2(uint64_t x) {
     return l;
 }
 
+// ---- large copies between device memory and PAGEABLE host memory -------------------------------------------------------
+// cudaMemcpy on pageable memory makes the driver stage every piece through its own small pinned buffer on one thread:
+// ~15 GB/s device->host and ~11 GB/s host->device on this box, against 57 / 56 GB/s for pinned memory -- 756 ms instead of
+// 199 ms for the outputs of a 2^20 x 135 commit (bench.py e2e_pageable, round-2 first measurement).  Callers that cannot
+// pin their buffers (a Vec<F> from the Rust allocator, a numpy array) get the same pipeline inside the library: the
+// copy engine moves 128 MB slots between HBM and a two-slot pinned ring at link speed while several host threads copy
+// the previous slot to / from the caller's memory.
+enum { STAGE_SLOT_LOG = 27 };  // 128 MB
+static const size_t kStageSlot = (size_t)1 << STAGE_SLOT_LOG;
+static const size_t kStageMin = (size_t)32 << 20;  // smaller copies are not worth the pipeline
+
+struct HostPiece {
+    char *ptr;
+    size_t bytes;
+};
+struct CopyTask {
+    char *dst;
+    const char *src;
+    size_t bytes;
+};
+
+void run_copy_tasks(std::vector<CopyTask> &tasks) {
+    // split into units of at most 4 MB so that the threads balance, then deal them out round robin
+    std::vector<CopyTask> units;
+    const size_t unit = (size_t)4 << 20;
+    for (const CopyTask &t : tasks)
+        for (size_t off = 0; off < t.bytes; off += unit) units.push_back(CopyTask{t.dst + off, t.src + off, std::min(unit, t.bytes - off)});
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned T = std::max(1u, std::min(8u, hw ? hw / 2 : 2u));
+    T = (unsigned)std::min<size_t>(T, units.size());
+    auto work = [&](unsigned t) {
+        for (size_t k = t; k < units.size(); k += T) memcpy(units[k].dst, units[k].src, units[k].bytes);
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; t++) th.emplace_back(work, t);
+    if (T) work(0);
+    for (auto &x : th) x.join();
+}
+
+int stage_ring_ready(p2g_ctx *ctx) {
+    if (ctx->stage_ring) return 0;
+    cudaError_t e = cudaHostAlloc(&ctx->stage_ring, 2 * kStageSlot, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ctx->stage_ring = nullptr;
+        return ctx->fail(P2G_ERR_OOM, "cudaHostAlloc of the staging ring failed: %s", cudaGetErrorString(e));
+    }
+    for (auto &ev : ctx->stage_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    return 0;
+}
+
+// The host side is the concatenation of `pieces` (a caller's columns need not be adjacent), the device side one
+// contiguous block.  Synchronous; `stream` must already be ordered behind whatever produces / consumes the device side.
+int staged_copy(p2g_ctx *ctx, const std::vector<HostPiece> &pieces, void *dev, bool to_host, cudaStream_t stream) {
+    int rc = stage_ring_ready(ctx);
+    if (rc) return rc;
+    char *ring = (char *)ctx->stage_ring;
+    size_t bytes = 0;
+    for (const HostPiece &hp : pieces) bytes += hp.bytes;
+    if (!bytes) return 0;
+    const size_t nchunks = (bytes + kStageSlot - 1) / kStageSlot;
+    auto len = [&](size_t i) { return std::min(kStageSlot, bytes - i * kStageSlot); };
+    // host <-> ring for chunk i: walk the pieces that overlap [i * slot, i * slot + len)
+    size_t piece = 0, piece_start = 0;  // cursor: pieces[piece] starts at byte piece_start of the concatenation
+    auto host_tasks = [&](size_t i, std::vector<CopyTask> &tasks) {
+        const size_t lo = i * kStageSlot, hi = lo + len(i);
+        while (piece < pieces.size() && piece_start + pieces[piece].bytes <= lo) piece_start += pieces[piece++].bytes;
+        size_t p = piece, ps = piece_start;
+        char *slot = ring + (i & 1) * kStageSlot;
+        while (p < pieces.size() && ps < hi) {
+            const size_t a = std::max(lo, ps), b = std::min(hi, ps + pieces[p].bytes);
+            if (b > a) {
+                char *h = pieces[p].ptr + (a - ps), *r = slot + (a - lo);
+                tasks.push_back(to_host ? CopyTask{h, r, b - a} : CopyTask{r, h, b - a});
+            }
+            ps += pieces[p++].bytes;
+        }
+    };
+    std::vector<CopyTask> tasks;
+    if (to_host) {
+        CK(cudaMemcpyAsync(ring, dev, len(0), cudaMemcpyDeviceToHost, stream));
+        CK(cudaEventRecord(ctx->stage_ev[0], stream));
+        for (size_t i = 0; i < nchunks; i++) {
+            if (i + 1 < nchunks) {  // the other slot was drained in the previous iteration
+                CK(cudaMemcpyAsync(ring + ((i + 1) & 1) * kStageSlot, (char *)dev + (i + 1) * kStageSlot, len(i + 1), cudaMemcpyDeviceToHost, stream));
+                CK(cudaEventRecord(ctx->stage_ev[(i + 1) & 1], stream));
+            }
+            CK(cudaEventSynchronize(ctx->stage_ev[i & 1]));
+            tasks.clear();
+            host_tasks(i, tasks);
+            run_copy_tasks(tasks);
+        }
+    } else {
+        for (size_t i = 0; i < nchunks; i++) {
+            if (i >= 2) CK(cudaEventSynchronize(ctx->stage_ev[i & 1]));  // the upload that last used this slot has left it
+            tasks.clear();
+            host_tasks(i, tasks);
+            run_copy_tasks(tasks);
+            CK(cudaMemcpyAsync((char *)dev + i * kStageSlot, ring + (i & 1) * kStageSlot, len(i), cudaMemcpyHostToDevice, stream));
+            CK(cudaEventRecord(ctx->stage_ev[i & 1], stream));
+        }
+        CK(cudaStreamSynchronize(stream));  // the ring is free again when this returns
+    }
+    return 0;
+}
+
 // device columns [first, last) -> the caller's per-column host buffers; buffers adjacent in host memory share one copy
 int copy_columns_home(p2g_ctx *ctx, void *const *dst, unsigned first, unsigned last, const void *src, size_t col_bytes,
                       cudaStream_t stream) {
@@ -841,6 +950,10 @@ void p2g_destroy(p2g_ctx *ctx) {
     for (auto &ev : ctx->gready) cudaEventDestroy(ev);
     for (auto &ev : ctx->gdone) cudaEventDestroy(ev);
     for (auto &ev : ctx->tev) cudaEventDestroy(ev);
+    if (ctx->stage_ring) {
+        cudaFreeHost(ctx->stage_ring);
+        for (auto &ev : ctx->stage_ev) cudaEventDestroy(ev);
+    }
     cudaStreamDestroy(ctx->h2d_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
@@ -1150,7 +1263,12 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
         const unsigned col0 = gi2 * group_cols, ncol = std::min(group_cols, c - col0);
         char *g_in = (char *)d_input + (size_t)col0 * col_bytes;
         char *g_co = (char *)d_coeffs + (size_t)col0 * col_bytes;
-        if (!dev_in) {
+        if (!dev_in && !pipelined && (size_t)ncol * col_bytes >= kStageMin && !is_pinned(d->col_ptrs[col0])) {
+            // pageable input: through the pinned ring on several host threads (staged_copy), not the driver's own staging
+            std::vector<HostPiece> pieces;
+            for (unsigned j = col0; j < col0 + ncol; j++) pieces.push_back(HostPiece{(char *)const_cast<void *>(d->col_ptrs[j]), col_bytes});
+            if ((rc = staged_copy(ctx, pieces, (char *)h2d_base + (size_t)col0 * col_bytes, false, st))) return rc;
+        } else if (!dev_in) {
             cudaStream_t up = pipelined ? hs : st;
             for (unsigned j = col0; j < col0 + ncol;) {
                 // columns that are adjacent in host memory (a 2-D array behind the pointer table) go up in one copy
@@ -1244,17 +1362,45 @@ int32_t p2g_commit(p2g_ctx *ctx, p2g_commit_desc *d) {
     CK(cudaEventRecord(ctx->ev[4], st));
 
     // ---- D2H
+    // Pageable destinations: every launch is enqueued by now, so this thread is free to pull the big outputs home
+    // through the pinned ring (staged_copy, on the copy stream) as soon as each is final -- the coefficients after the
+    // inverse NTT, the leaves after the LDE (while the tree is still being hashed), the digests after the tree.
+    bool coeffs_staged = false, leaves_staged = false, digests_staged = false;
     if (!dev_out) {
-        if (d->input_kind == P2G_INPUT_VALUES && d->coeffs_out && !coeffs_sent)
+        const size_t leaf_bytes_local = (size_t)rows_local * pitch_dev * f.elem;
+        if (values && d->coeffs_out && !coeffs_sent && (size_t)c * col_bytes >= kStageMin && !is_pinned(d->coeffs_out[0])) {
+            bool all = true;
+            for (unsigned j = 0; j < c; j++) all &= d->coeffs_out[j] != nullptr;
+            if (all) {
+                std::vector<HostPiece> pieces;
+                for (unsigned j = 0; j < c; j++) pieces.push_back(HostPiece{(char *)d->coeffs_out[j], col_bytes});
+                CK(cudaEventSynchronize(ctx->tev[3 * (num_groups - 1) + 1]));  // the last group's inverse NTT is done
+                if ((rc = staged_copy(ctx, pieces, d_coeffs, true, cs))) return rc;
+                coeffs_staged = true;
+            }
+        }
+        if (want_leaves && !leaves_sent && out_pitch == pitch_dev && leaf_bytes_local >= kStageMin && !is_pinned(d->leaves_out)) {
+            CK(cudaEventSynchronize(ctx->ev[3]));  // LDE (and salts) done; the sponge kernels read the same rows meanwhile
+            if ((rc = staged_copy(ctx, {HostPiece{(char *)d->leaves_out, leaf_bytes_local}}, d_leaves, true, cs))) return rc;
+            leaves_staged = true;
+        }
+        if (d->digests_out && num_digests_local * 32 >= kStageMin && !is_pinned(d->digests_out)) {
+            CK(cudaEventSynchronize(ctx->ev[4]));
+            if ((rc = staged_copy(ctx, {HostPiece{(char *)d->digests_out, (size_t)num_digests_local * 32}}, d_digests, true, cs))) return rc;
+            digests_staged = true;
+        }
+    }
+    if (!dev_out) {
+        if (d->input_kind == P2G_INPUT_VALUES && d->coeffs_out && !coeffs_sent && !coeffs_staged)
             if ((rc = copy_columns_home(ctx, d->coeffs_out, 0, c, d_coeffs, col_bytes, st))) return rc;
-        if (want_leaves && !leaves_sent) {
+        if (want_leaves && !leaves_sent && !leaves_staged) {
             if (out_pitch == pitch_dev)
                 CK(cudaMemcpyAsync(d->leaves_out, d_leaves, (size_t)rows_local * pitch_dev * f.elem, cudaMemcpyDeviceToHost, st));
             else
                 CK(cudaMemcpy2DAsync(d->leaves_out, out_pitch * f.elem, d_leaves, pitch_dev * f.elem, width * f.elem, rows_local,
                                      cudaMemcpyDeviceToHost, st));
         }
-        if (d->digests_out && num_digests_local)
+        if (d->digests_out && num_digests_local && !digests_staged)
             CK(cudaMemcpyAsync(d->digests_out, d_digests, num_digests_local * 32, cudaMemcpyDeviceToHost, st));
         if (d->cap_out) CK(cudaMemcpyAsync(d->cap_out, d_cap, num_cap_local * 32, cudaMemcpyDeviceToHost, st));
     } else if (keep) {
