@@ -99,9 +99,41 @@ __device__ __forceinline__ void gl_mul128(u64 a, u64 b, u64 &lo, u64 &hi) {
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
 }
 
+// a^2 with three products (a0^2, a0 a1, a1^2) and the cross term doubled by funnel shifts: one IMAD.WIDE and the
+// register-pair copies of the second cross product less, two shifts more.  Costed as a loss in round 1 (the ALU pipe is
+// the scarce one), measured as a gain in round 2: 27.32k -> 26.47k cycles per warp-permutation with the two squarings of
+// every S-box (tools/microbench/poseidon_bench.cu).
+__device__ __forceinline__ void gl_sqr128(u64 a, u64 &lo, u64 &hi) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32);
+    asm("{\n\t"
+        ".reg .u64 p0, p3, m, t;\n\t"
+        ".reg .u32 m0, m1, d0, d1, d2, z;\n\t"
+        "mul.wide.u32 p0, %2, %2;\n\t"
+        "mul.wide.u32 m, %2, %3;\n\t"
+        "mul.wide.u32 p3, %3, %3;\n\t"
+        "mov.b64 {m0, m1}, m;\n\t"
+        "shl.b32 d0, m0, 1;\n\t"
+        "shf.l.wrap.b32 d1, m0, m1, 1;\n\t"
+        "shr.b32 d2, m1, 31;\n\t"
+        "mov.u32 z, 0;\n\t"
+        "mov.b64 t, {z, d0};\n\t"
+        "add.cc.u64 %0, p0, t;\n\t"
+        "mov.b64 t, {d1, d2};\n\t"
+        "addc.u64 %1, p3, t;\n\t"
+        "}"
+        : "=l"(lo), "=l"(hi)
+        : "r"(a0), "r"(a1));
+}
+
 __device__ __forceinline__ u64 gl_mul(u64 a, u64 b) {
     u64 lo, hi;
     gl_mul128(a, b, lo, hi);
+    return gl_reduce128(lo, hi);
+}
+
+__device__ __forceinline__ u64 gl_sqr(u64 a) {
+    u64 lo, hi;
+    gl_sqr128(a, lo, hi);
     return gl_reduce128(lo, hi);
 }
 

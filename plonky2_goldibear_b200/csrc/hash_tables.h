@@ -21,8 +21,10 @@ struct PoseidonGlTables {
 };
 
 struct Poseidon2BbTables {
-    uint32_t ext_rc[8][16];  // Montgomery form; hash/poseidon2_babybear.rs:26-61
-    uint32_t int_rc[13];     // Montgomery form; hash/poseidon2_babybear.rs:63-67
+    // Montgomery form MINUS p as a wrapped 32-bit word: lane + entry is then a signed word in [-p, p + 2^15), which is what
+    // the S-box's signed multiplication chain takes (poseidon2_bb.cuh, p2bb_sbox_rc_signed)
+    uint32_t ext_rc[8][16];  // hash/poseidon2_babybear.rs:26-61
+    uint32_t int_rc[13];     // hash/poseidon2_babybear.rs:63-67
 };
 
 }  // namespace p2g

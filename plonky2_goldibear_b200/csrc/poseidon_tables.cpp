@@ -38,8 +38,8 @@ void build_poseidon_gl_tables(PoseidonGlTables *T) {
 
 void build_poseidon2_bb_tables(Poseidon2BbTables *T) {
     for (int r = 0; r < 8; r++)
-        for (int i = 0; i < 16; i++) T->ext_rc[r][i] = BbHost::to_internal(P2G_BB_P2_EXTERNAL_RC[r][i] % P2G_BB_P);
-    for (int r = 0; r < 13; r++) T->int_rc[r] = BbHost::to_internal(P2G_BB_P2_INTERNAL_RC[r] % P2G_BB_P);
+        for (int i = 0; i < 16; i++) T->ext_rc[r][i] = BbHost::to_internal(P2G_BB_P2_EXTERNAL_RC[r][i] % P2G_BB_P) - P2G_BB_P;
+    for (int r = 0; r < 13; r++) T->int_rc[r] = BbHost::to_internal(P2G_BB_P2_INTERNAL_RC[r] % P2G_BB_P) - P2G_BB_P;
 }
 
 }  // namespace p2g

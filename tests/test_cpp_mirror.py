@@ -51,3 +51,20 @@ def test_ntt_tile_code_on_the_host_matches_the_definition(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout[-4000:]
     assert "all ok" in res.stdout and "FAIL" not in res.stdout
+
+
+def test_poseidon2_bb_kernel_code_on_the_host_matches_the_oracle(tmp_path):
+    """The headers the BabyBear hash kernels are built from (field_bb.cuh, poseidon2_bb.cuh), compiled with g++: the
+    permutation with its signed S-box products and lazy internal rounds, every stated range asserted, against the
+    oracle on extreme, random and chained states."""
+    from oracle import p2o
+    p2o.load()
+    src = os.path.join(ROOT, "tests", "cpp", "poseidon2_bb_emul_test.cpp")
+    exe = str(tmp_path / "poseidon2_bb_emul_test")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    orc = os.path.join(ROOT, "oracle")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-Wno-attributes", "-Wno-unknown-pragmas", "-I", cuda_inc, "-I", orc, src, "-o", exe,
+                    "-L", orc, "-l:libp2o.so", "-Wl,-rpath," + orc], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, (res.stdout + res.stderr)[-4000:]
+    assert "all ok" in res.stdout

@@ -146,7 +146,10 @@ int main(int argc, char **argv) {
         cudaEventElapsedTime(&ms, e0, e1);
         if (ms < best) best = ms;
     }
-    printf("BB  block %d occ %d blocks/SM: %.3f ms for %zu perms -> %.1f M perm/s\n", BLOCK, occ, best, bthreads * chain,
-           bthreads * (double)chain / best * 1e-3);
+    u32 hb[16];
+    bb_chain<<<bthreads / BLOCK, BLOCK>>>(b_in, b_out, 3);
+    cudaMemcpy(hb, b_out, 64, cudaMemcpyDeviceToHost);  // compare across variants: three chained permutations of 0x01010101 words
+    printf("BB  block %d occ %d blocks/SM: %.3f ms for %zu perms -> %.1f M perm/s   out %08x %08x %08x %08x (%s)\n", BLOCK, occ, best,
+           bthreads * chain, bthreads * (double)chain / best * 1e-3, hb[0], hb[1], hb[14], hb[15], cudaGetErrorString(cudaGetLastError()));
     return ok ? 0 : 1;
 }
