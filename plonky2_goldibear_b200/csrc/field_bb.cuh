@@ -72,7 +72,8 @@ P2G_BB_FN u32 bb_mul(u32 a, u32 b) { return bb_monty_reduce((u64)a * b); }
 // IMAD.HI and one subtraction that either integer pipe can take -- where the unsigned form ends in a conditional
 // subtraction (VIADDMNMX) that only the half-rate ALU pipe executes.  Measured on the permutation (tools/microbench):
 // 3.51 -> 3.93 G permutations/s; pinning those subtractions to the multiplier pipe (an IMAD by a run-time -1) loses
-// 2-13 % of that again, so the choice of pipe is left to ptxas.  (A fused form -- the high word of a b - m p in one
+// 2-13 % of that again, and so does taking m off the multiplier pipe (low word * p^-1 as two shifts, an add and an
+// exclusive-or on the ALU pipe: 3.54-3.80 G/s, more registers), so the instruction choice is left as it is.  (A fused form -- the high word of a b - m p in one
 // IMAD.HI with a 64-bit addend, as ptxas builds for the unsigned reduction -- is not reachable for signed operands:
 // mad.wide.s32 with an addend is split into a product and a two-instruction 64-bit add.)
 P2G_BB_FN int bb_mul_signed(int a, int b) {

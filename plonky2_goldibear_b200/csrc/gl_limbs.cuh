@@ -144,9 +144,34 @@ P2G_HD void dft(int (&v)[1 << K][4]) {
 // 2^63.2, so a wrapped sum is more than 2^32 below the first operand), and the wrap folds back in as + (2^32 - 1).
 // `eps` = 2^32 - 1, handed in as a run-time value on purpose: with the literal, ptxas rewrites each multiply-add by
 // 0xffffffff into a four-instruction negate / high-product / carry sequence instead of one IMAD.WIDE.
+#ifndef P2G_FOLD96_VARIANT
+#define P2G_FOLD96_VARIANT 2
+#endif
 P2G_HD u64 fold96(u64 L, u64 H, u32 eps) {
 #if defined(__CUDA_ARCH__)
     u64 r;
+#if P2G_FOLD96_VARIANT == 2
+    // all on the ALU pipe: w2 (2^32 - 1) = (w2 << 32) - w2 is a subtraction from the low word and an addition to the high
+    // one; the multiplier pipe is the busier one in the NTT kernels (8 IMAD.WIDE per join before the fold)
+    (void)eps;
+    asm("{\n\t"
+        ".reg .u32 l0, l1, h0, h1, w1, w2, r0, r1, t;\n\t"
+        ".reg .pred q;\n\t"
+        "mov.b64 {l0, l1}, %1;\n\t"
+        "mov.b64 {h0, h1}, %2;\n\t"
+        "add.cc.u32 w1, l1, h0;\n\t"
+        "addc.u32 w2, h1, 0;\n\t"
+        "sub.cc.u32 r0, l0, w2;\n\t"
+        "subc.u32 t, w1, 0;\n\t"
+        "add.u32 r1, t, w2;\n\t"
+        "setp.lt.u32 q, r1, w1;\n\t"
+        "@q add.cc.u32 r0, r0, 0xffffffff;\n\t"
+        "@q addc.u32 r1, r1, 0;\n\t"
+        "mov.b64 %0, {r0, r1};\n\t"
+        "}"
+        : "=&l"(r)
+        : "l"(L), "l"(H));
+#else
     asm("{\n\t"
         ".reg .u32 l0, l1, h0, h1, w1, w2, r0, r1, e;\n\t"
         ".reg .u64 a;\n\t"
@@ -159,11 +184,18 @@ P2G_HD u64 fold96(u64 L, u64 H, u32 eps) {
         "mad.wide.u32 %0, w2, %3, a;\n\t"
         "mov.b64 {r0, r1}, %0;\n\t"
         "setp.lt.u32 q, r1, w1;\n\t"
+#if P2G_FOLD96_VARIANT == 0
         "selp.u32 e, 1, 0, q;\n\t"
         "mad.wide.u32 %0, e, %3, %0;\n\t"
+#else  // the wrap folded back in by two predicated adds on the ALU pipe instead of a third IMAD.WIDE
+        "@q add.cc.u32 r0, r0, 0xffffffff;\n\t"
+        "@q addc.u32 r1, r1, 0;\n\t"
+        "mov.b64 %0, {r0, r1};\n\t"
+#endif
         "}"
         : "=&l"(r)
         : "l"(L), "l"(H), "r"(eps));
+#endif
     return r;
 #else
     const u32 l0 = (u32)L, l1 = (u32)(L >> 32), h0 = (u32)H, h1 = (u32)(H >> 32);
