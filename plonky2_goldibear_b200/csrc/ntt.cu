@@ -64,6 +64,19 @@ struct NttBb {
     static __device__ __forceinline__ E mul(E a, E b) { return bb_mul(a, b); }
     static __device__ __forceinline__ E add(E a, E b) { return bb_add(a, b); }
     static __device__ __forceinline__ E sub(E a, E b) { return bb_sub(a, b); }
+    // (a - b) * w^e for a butterfly: table entry e = (w, w' = floor(w 2^32 / p)) with w CANONICAL -- Shoup's form of a
+    // product by a constant: q = floor(d w' / 2^32) is the quotient of d w by p up to one, so d w - q p lies in [0, 2p)
+    // for ANY d < 2^32, which lets the difference stay unreduced (a - b + p, one three-input add).  IMAD.HI + 2 IMAD
+    // (8 multiplier-pipe cycles) and one conditional subtraction, against IMAD.WIDE + IMAD + IMAD.HI (10) and two for
+    // the Montgomery product of a reduced difference.  The product is exact in integers, so words keep the
+    // representation they came in, as with the Montgomery-form constants of the other factors.
+    static __device__ __forceinline__ E mul_root(E a, E b, const E *roots, u32 e) {
+        const uint2 t = reinterpret_cast<const uint2 *>(roots)[e];
+        const u32 d = a - b + P2G_BB_P;
+        const u32 q = __umulhi(d, t.y);
+        const u32 r = d * t.x - q * P2G_BB_P;
+        return bb_min_u32(r, r - P2G_BB_P);
+    }
 };
 
 // base^e from the three-level power table (table building only)
@@ -102,19 +115,20 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// BabyBear keeps its in-tile roots (w^e, e < np/2) in shared memory behind the tile; Goldilocks reads its 32-byte join
+// BabyBear keeps its in-tile roots ((w^e, floor(w^e 2^32 / p)), e < np/2) in shared memory behind the tile; Goldilocks reads its 32-byte join
 // entries from the global table through the read-only path (tile_load_w4)
 template <class F>
 __host__ __device__ inline size_t roots_smem_bytes(u32 lp) {
-    return F::LIMBS ? 0 : (size_t)((1u << lp) >> 1) * sizeof(typename F::E);
+    return F::LIMBS ? 0 : (size_t)((1u << lp) >> 1) * 2 * sizeof(typename F::E);  // (w, w') pairs, NttBb::mul_root
 }
 template <class F>
 __device__ __forceinline__ const typename F::E *stage_roots(const NttPass &p, typename F::E *roots_s, u32 lp) {
     typedef typename F::E E;
     const E *roots = (const E *)p.roots;
     if (F::LIMBS) return roots;
-    const u32 cnt = (1u << lp) >> 1;
-    for (u32 k = threadIdx.x; k < cnt; k += blockDim.x) roots_s[k] = roots[k];
+    const u32 cnt = (1u << lp) >> 1;  // entries of two words
+    for (u32 k = threadIdx.x; k < cnt; k += blockDim.x)
+        reinterpret_cast<uint2 *>(roots_s)[k] = __ldg(reinterpret_cast<const uint2 *>(roots) + k);
     return roots_s;
 }
 

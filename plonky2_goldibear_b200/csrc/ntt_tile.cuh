@@ -15,7 +15,7 @@
 // straight to global memory (no separate store loop: a unit's outputs are whole 64-byte runs already).
 //   * Goldilocks: a unit is a multiplication-free 2^K-point DFT on 24-bit limbs (gl_limbs.cuh) and the round's twiddle
 //     w_L^(low k) rides in the join;
-//   * BabyBear: K radix-2 stages with Montgomery multiplications by table entries.
+//   * BabyBear: K radix-2 stages; the product (a - b) * w with a precomputed quotient (Shoup form, F::mul_root).
 //
 // The code in this header is plain C++ so that tests/cpp/ntt_tile_emul_test.cpp can run every tile kind on the host,
 // thread by thread, against a naive transform; the asynchronous / vectorised loads are the only device-only parts.
@@ -123,7 +123,7 @@ P2G_TILE_FN void tile_load_w4(const u64 *p, u64 (&W)[4]) {
 }
 
 // twiddle context of a tile.  roots: Goldilocks [np][4] in GLOBAL memory, entry e = w^e * 2^(24 i), i < 4 (the W_i of
-// the limb join, gl_limbs.cuh); BabyBear w^e for e < np/2 in shared memory.
+// the limb join, gl_limbs.cuh); BabyBear (w^e, floor(w^e 2^32 / p)) for e < np/2 in shared memory (F::mul_root).
 template <class F>
 struct TwCtx {
     typedef typename F::E E;
@@ -203,7 +203,7 @@ struct UnitTransform<F, false> {  // BabyBear: K radix-2 stages
                 const u32 e = (((j & (hj - 1)) << lowbits) | low) << s;
                 const E a = v[j], b = v[j + hj];
                 v[j] = F::add(a, b);
-                v[j + hj] = F::mul(F::sub(a, b), roots[e]);
+                v[j + hj] = F::mul_root(a, b, roots, e);  // (a - b) * w_np^e
             }
         }
         if (!LAST) {

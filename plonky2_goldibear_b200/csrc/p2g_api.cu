@@ -225,7 +225,8 @@ int get_root_table(p2g_ctx *ctx, const FieldInfo &f, unsigned lp, bool inverse, 
         return 0;
     }
     const bool gl = f.id == FIELD_GL;
-    size_t cnt = gl ? ((size_t)4 << lp) : (lp ? ((size_t)1 << (lp - 1)) : 1);
+    // Goldilocks: [np][4] join entries; BabyBear: [np/2] pairs (w, floor(w 2^32 / p)), w canonical (NttBb::mul_root)
+    size_t cnt = gl ? ((size_t)4 << lp) : 2 * (lp ? ((size_t)1 << (lp - 1)) : 1);
     std::vector<unsigned char> host(cnt * f.elem);
     uint64_t w = two_adic_generator(f, lp);
     if (inverse) w = f_inv(f, w);
@@ -241,8 +242,9 @@ int get_root_table(p2g_ctx *ctx, const FieldInfo &f, unsigned lp, bool inverse, 
             cur = f_mul(f, cur, w);
         }
     } else {
-        for (size_t k = 0; k < cnt; k++) {
-            store_elem(f, host.data(), k, f_internal(f, cur));
+        for (size_t k = 0; k < cnt / 2; k++) {
+            store_elem(f, host.data(), 2 * k, cur);
+            store_elem(f, host.data(), 2 * k + 1, (cur << 32) / P2G_BB_P);
             cur = f_mul(f, cur, w);
         }
     }

@@ -56,6 +56,18 @@ struct BbH {
     static E mul(E a, E b) { return redc((u64)a * b); }
     static E add(E a, E b) { return (u32)(((u64)a + b) % BB_P); }
     static E sub(E a, E b) { return (u32)(((u64)a + BB_P - b) % BB_P); }
+    // the device policy's Shoup-form butterfly product (csrc/ntt.cu, NttBb::mul_root), same 32-bit arithmetic
+    static E mul_root(E a, E b, const E *roots, u32 e) {
+        const u32 w = roots[2 * e], wq = roots[2 * e + 1];
+        const u32 d = a - b + BB_P;
+        const u32 q = (u32)(((u64)d * wq) >> 32);
+        const u32 r = d * w - q * BB_P;
+        if (r >= 2 * BB_P) {
+            std::printf("FAIL: Shoup product out of range\n");
+            std::exit(1);
+        }
+        return r >= BB_P ? r - BB_P : r;
+    }
     static u64 P() { return BB_P; }
     static u64 internal(u64 c) { return c * 268435454ull % BB_P; }  // Montgomery form
     static u64 canonical(u64 i) { return redc(i); }
@@ -143,14 +155,16 @@ static int run_case(unsigned log_n, const std::vector<unsigned> &lps, unsigned n
         {
             u64 w = F::root(lp);
             if (inverse) w = fpow<F>(w, F::P() - 2);
-            size_t cnt = F::LIMBS ? 4 * np : (np > 1 ? np / 2 : 1);
+            size_t cnt = F::LIMBS ? 4 * np : 2 * (np > 1 ? np / 2 : 1);
             keep.emplace_back(cnt);
             u64 cur = 1;
-            for (size_t k = 0; k < (F::LIMBS ? np : cnt); k++) {
-                if (F::LIMBS)
+            for (size_t k = 0; k < (F::LIMBS ? np : cnt / 2); k++) {
+                if (F::LIMBS) {
                     for (int i = 0; i < 4; i++) keep.back()[4 * k + i] = (E)fmul<F>(cur, fpow<F>(2, 24 * i));
-                else
-                    keep.back()[k] = (E)F::internal(cur);
+                } else {  // (w, floor(w 2^32 / p)), w canonical
+                    keep.back()[2 * k] = (E)cur;
+                    keep.back()[2 * k + 1] = (E)((cur << 32) / F::P());
+                }
                 cur = fmul<F>(cur, w);
             }
             p.roots = keep.back().data();
