@@ -687,10 +687,11 @@ def run_ours(args, field_name, check_only=False):
     roofline_ntt = {"kernels": "ntt_strided_kernel + ntt_final_natural_kernel + ntt_final_leaves_kernel", "bound": "hbm",
                     "achieved": ntt_bytes / t_ntt / 1e9, "peak": peak, "unit": "GB/s", "frac": ntt_bytes / t_ntt / 1e9 / peak,
                     "ms": t_ntt * 1e3, "algorithmic_gb": ntt_bytes / 1e9}
-    # integer-pipe view of the dominant kernel: issue cycles spent per warp-permutation against the SASS cost model
+    # integer-pipe view of the dominant kernel: cycles per warp-permutation against the pipe cost model (the costs that
+    # reproduce ncu's ALU and fmaheavy utilisation of this kernel: profiles/r2_leaf_sponge_cost_model.json)
     int_pipe = None
     try:
-        model = json.load(open(os.path.join(ROOT, "profiles", "r1_leaf_sponge_cost_model.json")))
+        model = json.load(open(os.path.join(ROOT, "profiles", "r2_leaf_sponge_cost_model.json")))
         key = "goldilocks_poseidon" if field_name == "gl" else "babybear_poseidon2"
         sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         clk = (clocks or {}).get("sm_mhz") or 1965.0
@@ -698,14 +699,14 @@ def run_ours(args, field_name, check_only=False):
         measured = t_leaf * sms * 4 * clk * 1e6 / (leaf_perms / 32.0)
         ref = model[key]
         dyn = ref["dynamic_instructions_per_permutation"]
-        alu, fma = 2.0 * dyn["ALU pipe"], 2.0 * dyn["IMAD.WIDE/HI"] + 1.0 * dyn["other IMAD"]
+        alu, mul = 2.0 * dyn["ALU pipe"], 4.0 * dyn["IMAD.WIDE/HI"] + 2.0 * dyn["other IMAD"]
         int_pipe = {"kernel": "leaf_hash_kernel", "cycles_per_warp_permutation": measured,
                     "microbench_cycles_per_warp_permutation": ref["measured_cycles_per_warp_permutation"],
-                    "alu_pipe_cycles": alu, "fma_pipe_cycles": fma,
-                    "busier_pipe_share_of_time": max(alu, fma) / measured,
-                    "model": "profiles/r1_leaf_sponge_cost_model.json: SASS instruction counts per permutation x 2 cycles per ALU-pipe instruction, "
-                             "2 per IMAD.WIDE/HI, 1 per other IMAD (the costs that reproduce ncu's pipe utilisation of this kernel: the integer ALU pipe "
-                             "is half rate on B200 and the scarce one; the pipes run concurrently)"}
+                    "alu_pipe_cycles": alu, "multiplier_pipe_cycles": mul,
+                    "busier_pipe_share_of_time": max(alu, mul) / measured,
+                    "model": "profiles/r2_leaf_sponge_cost_model.json: dynamic warp instructions per permutation (ncu source page) x 2 cycles per "
+                             "ALU-pipe instruction, 2 per IMAD of any kind and 4 per IMAD.WIDE/HI on the multiplier pipe (ncu: fmaheavy) -- the "
+                             "multiplier pipe is the busiest pipe of the kernel (ncu 88 % Goldilocks, 85 % BabyBear); the pipes run concurrently"}
     except Exception as e:  # the model file is evidence, not a dependency
         int_pipe = {"unavailable": str(e)}
     line = {
