@@ -190,6 +190,8 @@ def workload_config(args, field_name):
             "field": field_name, "log_rows": args.log_n, "cols": args.cols, "rate_bits": args.rate_bits,
             "cap_height": args.cap_height, "parallelism": "coset-sharded x%d" % args.gpus if args.gpus > 1 else "single GPU",
             "exchange": (args.exchange if args.gpus > 1 else None),
+            "exchange_transport": ((os.environ.get("P2G_EXCHANGE") or ("fused peer stores" if args.gpus == 2 else "block push kernel behind the inverse NTT"))
+                                   if args.gpus > 1 and args.exchange in ("fused", "pipelined") else None),
             "l2": "inputs (%.2f GB) and leaves (%.2f GB) are larger than the 126 MB L2; no flush needed" % (
                 args.cols * (1 << args.log_n) * (8 if field_name == "gl" else 4) / 1e9,
                 args.cols * ((1 << args.rate_bits) << args.log_n) * (8 if field_name == "gl" else 4) / 1e9)}

@@ -359,6 +359,45 @@ void launch_build_scale_table(int field, void *out, uint32_t log_np, uint32_t lo
     ++*launches;
 }
 
+// the finished coefficient block to every peer: each thread moves 4 x 16 bytes per trip, a warp instruction stores 512
+// contiguous bytes into one peer's buffer (plain stores to peer-mapped memory, NVLink / NVSwitch)
+struct PeerList {
+    uint4 *p[8];
+    unsigned n;
+};
+__global__ void __launch_bounds__(256) peer_push_kernel(const uint4 *__restrict__ src, PeerList peers, size_t n16) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        const uint4 a = __ldg(src + i), b = __ldg(src + i + stride), c = __ldg(src + i + 2 * stride), d = __ldg(src + i + 3 * stride);
+        for (unsigned k = 0; k < peers.n; k++) {
+            uint4 *q = peers.p[k];
+            q[i] = a;
+            q[i + stride] = b;
+            q[i + 2 * stride] = c;
+            q[i + 3 * stride] = d;
+        }
+    }
+    for (; i < n16; i += stride) {
+        const uint4 a = __ldg(src + i);
+        for (unsigned k = 0; k < peers.n; k++) peers.p[k][i] = a;
+    }
+}
+void launch_peer_push(const void *src, void *const *peers, unsigned num_peers, size_t bytes, cudaStream_t stream, uint64_t *launches) {
+    PeerList pl;
+    pl.n = num_peers < 8 ? num_peers : 8;
+    for (unsigned k = 0; k < pl.n; k++) pl.p[k] = (uint4 *)peers[k];
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t n16 = bytes / 16;
+    size_t blocks = (n16 + 255) / 256;
+    if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
+    if (!blocks) return;
+    peer_push_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const uint4 *)src, pl, n16);
+    ++*launches;
+}
+
 void launch_salt_scatter(int field, const void *salts, uint32_t num_salt, uint32_t log_N, uint64_t row_begin,
                          uint64_t row_count, void *leaves, uint64_t pitch, uint32_t col0, cudaStream_t stream,
                          uint64_t *launches) {

@@ -355,6 +355,26 @@ static bool multi_pass(unsigned log_n) {  // the strided passes of a forward tra
     return P > 1;
 }
 
+// How the coefficients of a column-sharded inverse transform reach the other devices' gather buffers:
+//   0 "fused": the last pass stores every 64-byte run into the peers' buffers as well (NttPass::peer_dst) -- the transfer
+//      hides behind the butterflies while there are enough of them (2 devices: 67 columns each);
+//   1 "push": the last pass stores locally and a copy kernel sends the finished block (whole columns, contiguous) with
+//      16 bytes per lane, 512 contiguous bytes per warp instruction -- with 4 or 8 devices a device transforms 34 / 17
+//      columns and sends 3 / 7 times that, the kernel is store-bound, and 64-byte runs to seven targets reach ~500 GB/s
+//      of the link's 900;
+//   2 "ce": the same block through the copy engines, one copy per peer.
+// P2G_EXCHANGE=fused|push|ce overrides the choice.
+static int exchange_mode(unsigned num_peers, bool sendable) {  // sendable: one contiguous, 16-byte aligned block
+    if (!num_peers) return 0;
+    int mode = num_peers >= 3 ? 1 : 0;
+    if (const char *e = getenv("P2G_EXCHANGE")) {
+        if (!strcmp(e, "fused")) mode = 0;
+        else if (!strcmp(e, "push")) mode = 1;
+        else if (!strcmp(e, "ce")) mode = 2;
+    }
+    return sendable ? mode : 0;
+}
+
 // Runs size-2^log_n transforms over `num_cols` columns.
 //   inverse: values -> coefficients (natural order, scaled by 1/n), result in `dst` (column-major, user repr); nb = 1
 //   forward: nb coset LDE blocks in one launch per pass: coefficients (user repr, `src`) scaled by powers of
@@ -367,6 +387,7 @@ int run_transform_batch(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse
     unsigned lps[3], P;
     plan_passes(log_n, lps, &P);
     const uint64_t n = (uint64_t)1 << log_n;
+    int xmode = 0;
     if (nb == 0 || nb > 8 || (inverse && nb != 1)) return ctx->fail(P2G_ERR_INVALID, "bad transform batch %u", nb);
     unsigned log_min = log_n;
     const void *cur_src = src;
@@ -414,8 +435,13 @@ int run_transform_batch(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse
             p.dst_col_stride = dst_stride;
             p.out_user_repr = 1;
             if (inverse) {
-                for (unsigned k = 0; k < num_peers && k < 8; k++) p.peer_dst[k] = peer_dst[k];
-                p.num_peers = num_peers;
+                bool sendable = dst_stride == n && ((size_t)num_cols * n * f.elem) % 16 == 0 && (uintptr_t)dst % 16 == 0;
+                for (unsigned k = 0; k < num_peers && k < 8; k++) sendable = sendable && (uintptr_t)peer_dst[k] % 16 == 0;
+                xmode = exchange_mode(num_peers, sendable);
+                if (xmode == 0) {
+                    for (unsigned k = 0; k < num_peers && k < 8; k++) p.peer_dst[k] = peer_dst[k];
+                    p.num_peers = num_peers;
+                }
                 const uint64_t n_inv = f_pow(f, f_inv(f, 2), log_n);  // n^-1 = (1/2)^lg n, fft.rs:78
                 if (f.id == FIELD_GL) {
                     // n^-1 is a power of two here: it rides in the last round's join (gl_limbs.cuh) for free
@@ -430,6 +456,15 @@ int run_transform_batch(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse
                 p.row_batch_stride = row_stride;
                 launch_ntt_pass(f.id, repr, NTT_FINAL_LEAVES, p, ctx->stream, &ctx->launches);
             }
+        }
+    }
+    if (inverse && num_peers && xmode) {
+        // the coefficient block of this device (num_cols whole columns, contiguous) goes to the peers behind the last pass
+        const size_t bytes = (size_t)num_cols * n * f.elem;
+        if (xmode == 1) {
+            launch_peer_push(dst, peer_dst, num_peers, bytes, ctx->stream, &ctx->launches);
+        } else {
+            for (unsigned k = 0; k < num_peers; k++) CK(cudaMemcpyAsync(peer_dst[k], dst, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         }
     }
     cudaError_t e = cudaGetLastError();

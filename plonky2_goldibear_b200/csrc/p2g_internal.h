@@ -90,6 +90,9 @@ struct NttPass {
 };
 enum NttKind { NTT_STRIDED = 0, NTT_FINAL_NATURAL = 1, NTT_FINAL_LEAVES = 2 };
 void launch_ntt_pass(int field, int repr, int kind, const NttPass &p, cudaStream_t stream, uint64_t *launches);
+// dst_k[i] = src[i] for every peer buffer k (16-byte pieces; bytes a multiple of 16): the exchange step of a column-sharded
+// inverse transform when it is sent as one block (p2g_api.cu, exchange_mode)
+void launch_peer_push(const void *src, void *const *peers, unsigned num_peers, size_t bytes, cudaStream_t stream, uint64_t *launches);
 // fills tw_tables / scale_tables entries from three-level power tables ([3][1024], base^(k*1024^level)):
 //   tw_table[f*m_out + j0] = wpow^(f*j0) * (spow ? spow^j0 : 1);   scale_table[i] = spow^(i << log_mout)
 void launch_build_tw_table(int field, void *out, uint32_t log_min, uint32_t log_np, const void *wpow, const void *spow,

@@ -721,6 +721,31 @@ def test_multi_device_context_commit_matches_oracle(oracle, field, log_n, c, r, 
             mctx.close()
 
 
+@pytest.mark.parametrize("mode", ["fused", "push", "ce"])
+def test_multi_device_exchange_modes_match_oracle(oracle, monkeypatch, mode):
+    """The three ways the column-sharded inverse NTT hands its coefficients to the other devices (peer stores fused into
+    the last pass, a 16-byte-per-lane copy kernel behind it, the copy engines -- P2G_EXCHANGE), each forced, on 2 and 4
+    shards: identical outputs.  Odd sizes (a 2-row Goldilocks column is one 16-byte piece, a 1-row one is not sendable
+    as a block and must fall back to the fused stores)."""
+    import plonky2_goldibear_b200 as p2g
+    monkeypatch.setenv("P2G_EXCHANGE", mode)
+    for field, log_n, c, r, h in [(0, 12, 135, 3, 4), (1, 11, 70, 3, 3), (0, 1, 5, 2, 2), (0, 0, 7, 2, 2), (1, 1, 6, 2, 2)]:
+        F = fields()[field]
+        vals = synthetic_columns(F.order, F.dtype, c, 1 << log_n, seed=77)
+        ref = oracle.commit(field, vals, oracle.VALUES, r, h)
+        for devs in _device_lists():
+            if len(devs) > (1 << r) or (1 << h) < len(devs):
+                continue
+            mctx = p2g.Context(devs)
+            try:
+                b = p2g.PolynomialBatch.from_values(F, list(vals), r, False, h, ctx=mctx)
+                assert (np.stack(b.polynomials) == ref["coeffs"]).all(), (mode, devs)
+                assert (b.merkle_tree.leaves == ref["leaves"]).all(), (mode, devs)
+                assert (b.merkle_tree.cap.hashes == ref["cap"]).all(), (mode, devs)
+            finally:
+                mctx.close()
+
+
 def test_multi_device_context_rejects_what_it_cannot_shard(oracle):
     import plonky2_goldibear_b200 as p2g
     F = fields()[0]
