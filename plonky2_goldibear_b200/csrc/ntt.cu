@@ -141,42 +141,70 @@ __device__ __forceinline__ void run_rounds(const Tile &t, E *x, const E *roots_s
     }
 }
 
-// element-sized asynchronous copies for the transposing loads
-template <int BYTES>
-__device__ __forceinline__ void cp_async_elem(void *smem, const void *gmem) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sa), "l"(gmem), "n"(BYTES) : "memory");
+// ---- bulk tile load of the two final kinds (TMA unit, cp.async.bulk + mbarrier) -------------------------------------------
+// A final tile is 2^lw contiguous runs of np elements (chunks of a column / the same chunk of adjacent columns) and is
+// kept column-major in shared memory (ntt_tile.cuh), so each run is ONE bulk copy issued by one thread: no per-element
+// LDGSTS (np x 2^lw of them per tile before: 6 % of the Goldilocks and 18 % of the BabyBear final kernels' issue slots,
+// shared-memory store wavefronts on top), no registers, and the copy engine of the SM completes the mbarrier.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem, const void *gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+                 "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
 }
 
-// transposing tile load for the two final kinds: interleaved transform w is a contiguous run of np elements at
-// base(w), tile element (i, w) sits at x[(i << lw) + w].  A thread keeps its w (the block size is a multiple of the
-// tile width) and walks along the run; consecutive threads take consecutive w, so a warp fills whole tile rows
-// (conflict-free) and reads 32-byte pieces of 8 (Goldilocks) / 8-byte pieces of 16 (BabyBear) runs.  Element-sized
-// LDGSTS: no registers, the whole tile is in flight at once.
+// Starts the load of a column-major tile: column w (< live_w) = np elements at base_of(w), the other columns zero.
+// bulk: every run is 16-byte aligned and a multiple of 16 bytes long (NttPass::async_ok and np * sizeof(E) % 16 == 0);
+// otherwise plain loads.  tile_load_wait() (all threads) before the first round.
 template <class E, class BaseOf>
-__device__ __forceinline__ void load_transposed(E *x, u32 lp, u32 lw, u32 live_w, bool aligned16, const BaseOf &base_of) {
-    const u32 W = 1u << lw;
-    (void)aligned16;  // (16-byte vector loads scattered from registers were measured for the 4-byte field: LDE of 2^22 x 256
-    // 82.9 against 81.7 ms -- fewer shared-memory wavefronts, but the loads then wait in registers instead of in flight)
-    const u32 w = threadIdx.x & (W - 1);
-    const u32 i0 = threadIdx.x >> lw, istep = blockDim.x >> lw;
-    const u32 np = 1u << lp;
-    E *sm = x + ((size_t)i0 << lw) + w;
-    const u32 s_step = istep << lw;
-    if (w < live_w) {
-        const E *g = base_of(w) + i0;
-#pragma unroll 8
-        for (u32 i = i0; i < np; i += istep) {
-            cp_async_elem<(int)sizeof(E)>(sm, g);
-            g += istep;
-            sm += s_step;
+__device__ __forceinline__ void tile_load_columns(E *x, unsigned long long *bar, u32 lp, u32 lw, u32 cs, u32 live_w, bool bulk,
+                                                  const BaseOf &base_of) {
+    const u32 np = 1u << lp, W = 1u << lw;
+    if (bulk) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const u32 bytes = np * (u32)sizeof(E);
+            mbar_arrive_expect_tx(bar, live_w * bytes);
+            for (u32 w = 0; w < live_w; w++) bulk_load(x + (size_t)w * cs, base_of(w), bytes, bar);
         }
+        for (u32 idx = threadIdx.x; idx < ((W - live_w) << lp); idx += blockDim.x)
+            x[(size_t)(live_w + (idx >> lp)) * cs + (idx & (np - 1))] = (E)0;
     } else {
-        for (u32 i = i0; i < np; i += istep) {
-            *sm = (E)0;
-            sm += s_step;
+        for (u32 idx = threadIdx.x; idx < (W << lp); idx += blockDim.x) {
+            const u32 w = idx >> lp, i = idx & (np - 1);
+            x[(size_t)w * cs + i] = w < live_w ? base_of(w)[i] : (E)0;
         }
     }
+}
+__device__ __forceinline__ void tile_load_wait(unsigned long long *bar, bool bulk) {
+    if (bulk) mbar_wait(bar, 0);
+    __syncthreads();
+}
+template <class F>
+__host__ __device__ inline bool bulk_ok(const NttPass &p) {
+    return p.async_ok && (((size_t)sizeof(typename F::E) << p.log_np) % 16 == 0);
+}
+// the mbarrier sits behind the tile and the staged roots (both multiples of 8 bytes)
+template <class F>
+__host__ __device__ inline size_t final_smem_bytes(u32 lp, u32 lw) {
+    return ((size_t)tile_col_stride((u32)sizeof(typename F::E), lp, lw) << lw) * sizeof(typename F::E) + roots_smem_bytes<F>(lp) + 8;
 }
 
 template <class F, int DIR>
@@ -220,10 +248,11 @@ __global__ void __launch_bounds__(256, F::MIN_CTAS) ntt_final_natural_kernel(con
     E *x = reinterpret_cast<E *>(smem_raw);
     const NaturalTile<F, DIR> t(p, blockIdx.x);
     E *roots_s = x + t.tile_elems();
-    load_transposed<E>(x, t.lp, t.lw, 1u << t.lw, p.async_ok != 0, [&](u32 w) { return t.chunk(w); });
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw + final_smem_bytes<F>(t.lp, t.lw) - 8);
+    const bool bulk = bulk_ok<F>(p);
+    tile_load_columns<E>(x, bar, t.lp, t.lw, t.cs, 1u << t.lw, bulk, [&](u32 w) { return t.chunk(w); });
     const E *roots = stage_roots<F>(p, roots_s, t.lp);
-    cp_async_wait_all();
-    __syncthreads();
+    tile_load_wait(bar, bulk);
     run_rounds(t, x, roots);
 }
 
@@ -234,10 +263,11 @@ __global__ void __launch_bounds__(256, F::MIN_CTAS) ntt_final_leaves_kernel(cons
     E *x = reinterpret_cast<E *>(smem_raw);
     const LeavesTile<F, DIR> t(p, blockIdx.x);
     E *roots_s = x + t.tile_elems();
-    load_transposed<E>(x, t.lp, t.lw, t.ncols, p.async_ok != 0, [&](u32 w) { return t.src + (size_t)w * t.src_col_stride; });
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw + final_smem_bytes<F>(t.lp, t.lw) - 8);
+    const bool bulk = bulk_ok<F>(p);
+    tile_load_columns<E>(x, bar, t.lp, t.lw, t.cs, t.ncols, bulk, [&](u32 w) { return t.src + (size_t)w * t.src_col_stride; });
     const E *roots = stage_roots<F>(p, roots_s, t.lp);
-    cp_async_wait_all();
-    __syncthreads();
+    tile_load_wait(bar, bulk);
     run_rounds(t, x, roots);
 }
 
@@ -306,14 +336,14 @@ static void launch_pass_t(int kind, const NttPass &p, cudaStream_t stream, uint6
         u32 lc = p.log_n - lp;
         u32 wl = tile_width_log(F::W_LOG, lp);
         u32 lw = lc < wl ? lc : wl;
-        size_t smem = ((size_t)np << lw) * sizeof(E) + roots_bytes;
+        size_t smem = final_smem_bytes<F>(lp, lw);
         u64 tiles = NaturalTile<F, 1>::num_tiles(p);
         // natural order is the inverse transform's output, the leaf matrix the forward transform's: one direction each
         allow_large_smem((const void *)ntt_final_natural_kernel<F, 1>);
         ntt_final_natural_kernel<F, 1><<<(unsigned)tiles, block_threads((u64)np << lw), smem, stream>>>(p);
     } else {
         u32 wl = tile_width_log(F::W_LOG, lp);
-        size_t smem = ((size_t)np << wl) * sizeof(E) + roots_bytes;
+        size_t smem = final_smem_bytes<F>(lp, wl);
         u64 tiles = (u64)LeavesTile<F, 0>::num_tiles(p) * nb;
         allow_large_smem((const void *)ntt_final_leaves_kernel<F, 0>);
         ntt_final_leaves_kernel<F, 0><<<(unsigned)tiles, block_threads((u64)np << wl), smem, stream>>>(p);

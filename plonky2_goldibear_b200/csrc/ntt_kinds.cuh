@@ -82,7 +82,7 @@ struct StridedTile {
         tc.eps = eps;
         LoadFix<F> fix = {scale, user_repr};
         StridedEpi<F> epi = {dst, tw, lp, lw, lmo, jt};
-        tile_run_round<F, DIR>(r, pl, x, tc, lw, fix, epi, tid, nthreads);
+        tile_run_round<F, DIR, false>(r, pl, x, tc, lw, 0, fix, epi, tid, nthreads);
     }
 };
 
@@ -93,7 +93,7 @@ struct NaturalTile {
     E *dst;
     const NttPass *pp;
     size_t peer_off;
-    u32 lp, lc, lw, d0, lp1, lp2;
+    u32 lp, lc, lw, cs, d0, lp1, lp2;
     bool user_repr;
     u32 eps;
     TilePlan pl;
@@ -104,6 +104,7 @@ struct NaturalTile {
         lc = p.log_n - lp;  // log2(chunks per column)
         const u32 wl = tile_width_log(F::W_LOG, lp);
         lw = lc < wl ? lc : wl;  // chunks per tile
+        cs = tile_col_stride((u32)sizeof(E), lp, lw);
         const u32 groups_per_col = 1u << (lc - lw);
         const u32 col = block / groups_per_col;
         const u32 g = block - col * groups_per_col;
@@ -123,14 +124,14 @@ struct NaturalTile {
         const u32 lw = lc < wl ? lc : wl;
         return (1u << (lc - lw)) * p.num_cols;
     }
-    P2G_TILE_FN u32 tile_elems() const { return 1u << (lp + lw); }
+    P2G_TILE_FN u32 tile_elems() const { return cs << lw; }  // storage: 2^lw padded columns
     // interleaved transform w is the contiguous chunk natural_to_chunk(d0 + w) of the column
     P2G_TILE_FN const E *chunk(u32 w) const { return src + ((size_t)natural_to_chunk(d0 + w, lp1, lp2) << lp); }
     P2G_TILE_FN void load_scalar(E *x, u32 tid, u32 nthreads) const {
-        const u32 total = tile_elems(), W = 1u << lw;
+        const u32 total = 1u << (lp + lw), W = 1u << lw;
         for (u32 idx = tid; idx < total; idx += nthreads) {
             const u32 w = idx & (W - 1), i = idx >> lw;
-            x[idx] = chunk(w)[i];
+            x[(size_t)w * cs + i] = chunk(w)[i];
         }
     }
     P2G_TILE_FN void round(u32 r, E *x, const E *roots_s, u32 tid, u32 nthreads) const {
@@ -144,7 +145,7 @@ struct NaturalTile {
         LoadFix<F> fix = {nullptr, user_repr};
         NaturalEpi<F> epi = {dst, (E *const *)p.peer_dst, peer_off, p.num_peers, lp, lc, d0, (E)p.final_scale,
                              p.use_final_scale != 0, p.out_user_repr != 0};
-        tile_run_round<F, DIR>(r, pl, x, tc, lw, fix, epi, tid, nthreads);
+        tile_run_round<F, DIR, true>(r, pl, x, tc, lw, cs, fix, epi, tid, nthreads);
     }
 };
 
@@ -155,7 +156,7 @@ struct LeavesTile {
     E *rows;       // leaf (first row of the chunk, col0)
     const E *scale;
     size_t src_col_stride, pitch;
-    u32 lp, lw, ncols;
+    u32 lp, lw, cs, ncols;
     bool user_repr, out_user;
     u32 eps;
     TilePlan pl;
@@ -165,6 +166,7 @@ struct LeavesTile {
         lp = p.log_np;
         const u32 lc = p.log_n - lp;
         lw = tile_width_log(F::W_LOG, lp);  // columns per tile
+        cs = tile_col_stride((u32)sizeof(E), lp, lw);
         const u32 W = 1u << lw;
         const u32 col_groups = (p.num_cols + W - 1) >> lw;
         const u32 q = bs.tile / col_groups;
@@ -189,13 +191,13 @@ struct LeavesTile {
         const u32 lw = tile_width_log(F::W_LOG, lp);
         return ((p.num_cols + (1u << lw) - 1) >> lw) << lc;
     }
-    P2G_TILE_FN u32 tile_elems() const { return 1u << (lp + lw); }
+    P2G_TILE_FN u32 tile_elems() const { return cs << lw; }  // storage: 2^lw padded columns
     // unused column slots of a ragged last tile hold zeros
     P2G_TILE_FN void load_scalar(E *x, u32 tid, u32 nthreads) const {
-        const u32 total = tile_elems(), W = 1u << lw;
+        const u32 total = 1u << (lp + lw), W = 1u << lw;
         for (u32 idx = tid; idx < total; idx += nthreads) {
             const u32 w = idx & (W - 1), i = idx >> lw;
-            x[idx] = w < ncols ? src[(size_t)w * src_col_stride + i] : (E)0;
+            x[(size_t)w * cs + i] = w < ncols ? src[(size_t)w * src_col_stride + i] : (E)0;
         }
     }
     P2G_TILE_FN void round(u32 r, E *x, const E *roots_s, u32 tid, u32 nthreads) const {
@@ -205,7 +207,7 @@ struct LeavesTile {
         tc.eps = eps;
         LoadFix<F> fix = {scale, user_repr};
         LeavesEpi<F> epi = {rows, pitch, ncols, out_user};
-        tile_run_round<F, DIR>(r, pl, x, tc, lw, fix, epi, tid, nthreads);
+        tile_run_round<F, DIR, true>(r, pl, x, tc, lw, cs, fix, epi, tid, nthreads);
     }
 };
 

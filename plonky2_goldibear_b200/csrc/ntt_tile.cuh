@@ -4,11 +4,15 @@
 // Replaces, on the GPU, the butterfly loops of fft_classic (field/src/fft.rs:168-205) together with the
 // transpose + reverse_index_bits step of from_coeffs (fri/oracle.rs:108-118); see ntt.cu for the pass structure.
 //
-// Tile layout (all three kinds): element (i, w) at x[(i << lw) + w] -- i = point index inside the tile's transform
-// (0 .. np-1), w = which of the 2^lw interleaved transforms (columns / offsets / chunks).  A row i is one 64-byte run,
-// consecutive threads take consecutive w, so every shared-memory access of a warp is a set of whole rows: conflict-free
-// in every round but the last one (two rows of equal parity per half-warp there: 2-way).  The round-1 kernels kept the
-// contiguous tiles column-major and paid 8-way conflicts in two of three rounds.
+// Tile layout: i = point index inside the tile's transform (0 .. np-1), w = which of the 2^lw interleaved transforms
+// (columns / offsets / chunks); consecutive threads take consecutive w in every kind.
+//   * strided kind, row-major: element (i, w) at x[(i << lw) + w].  A row i is one 64-byte run of global memory, every
+//     shared-memory access of a warp is a set of whole rows: conflict-free in every round but the last one (two rows of
+//     equal parity per half-warp there: 2-way).
+//   * final kinds, column-major with a padded column stride: x[w * cs + i], cs = np + pad (tile_col_stride).  A column is
+//     one contiguous run of global memory and arrives as one bulk copy; the pad puts the columns a bank group apart, so
+//     a warp (8 w x 2 or 4 consecutive i) is conflict-free exactly where the row-major form is.  (The round-1 kernels
+//     were column-major WITHOUT the pad and with lanes along i: 8-way conflicts in two of three rounds.)
 //
 // A round = a thread takes the 2^K points that differ in the K position bits of the round ("unit"), transforms them in
 // registers and puts them back; the LAST round hands its outputs to the tile kind's epilogue, which stores them
@@ -213,8 +217,10 @@ struct UnitTransform<F, false> {  // BabyBear: K radix-2 stages
     }
 };
 
-template <class F, int K, int DIR, bool FIRST, bool LAST, class Epi>
-P2G_TILE_FN void tile_round(typename F::E *x, const TwCtx<F> &tc, u32 lw, u32 s0, const LoadFix<F> &fix, const Epi &epi,
+// cs = 0: row-major tile, element (i, w) at x[(i << lw) + w] (strided kind); cs > 0: column-major, x[w * cs + i] (the
+// final kinds, p2g_internal.h tile_col_stride).  The thread -> (w, unit) map is the same for both.
+template <class F, int K, int DIR, bool FIRST, bool LAST, bool COLMAJ, class Epi>
+P2G_TILE_FN void tile_round(typename F::E *x, const TwCtx<F> &tc, u32 lw, u32 cs, u32 s0, const LoadFix<F> &fix, const Epi &epi,
                             u32 tid, u32 nthreads) {
     typedef typename F::E E;
     constexpr u32 R = 1u << K;
@@ -225,8 +231,8 @@ P2G_TILE_FN void tile_round(typename F::E *x, const TwCtx<F> &tc, u32 lw, u32 s0
         const u32 w = u & ((1u << lw) - 1), t = u >> lw;
         const u32 low = t & ((1u << lowbits) - 1), hi = t >> lowbits;
         const u32 p0 = (hi << (lp - s0)) | low;
-        E *base = x + ((size_t)p0 << lw) + w;
-        const u32 stride = 1u << (lowbits + lw);
+        E *base = COLMAJ ? x + (size_t)w * cs + p0 : x + ((size_t)p0 << lw) + w;
+        const u32 stride = COLMAJ ? 1u << lowbits : 1u << (lowbits + lw);
         E v[R];
         typename Epi::template Pre<LAST ? K : 0> pre;
         if (LAST) epi.template prefetch<K>(p0, w, pre);
@@ -239,12 +245,12 @@ P2G_TILE_FN void tile_round(typename F::E *x, const TwCtx<F> &tc, u32 lw, u32 s0
 }
 
 // round r of the tile's plan (the caller separates rounds by a CTA barrier)
-template <class F, int DIR, class Epi>
-P2G_TILE_FN void tile_run_round(u32 r, const TilePlan &pl, typename F::E *x, const TwCtx<F> &tc, u32 lw,
+template <class F, int DIR, bool COLMAJ, class Epi>
+P2G_TILE_FN void tile_run_round(u32 r, const TilePlan &pl, typename F::E *x, const TwCtx<F> &tc, u32 lw, u32 cs,
                                 const LoadFix<F> &fix, const Epi &epi, u32 tid, u32 nthreads) {
     const bool first = r == 0, last = r + 1 == pl.nrounds;
     const u32 s0 = pl.s0(r), K = pl.K(r);
-#define P2G_ROUND(KK, FI, LA) tile_round<F, KK, DIR, FI, LA, Epi>(x, tc, lw, s0, fix, epi, tid, nthreads)
+#define P2G_ROUND(KK, FI, LA) tile_round<F, KK, DIR, FI, LA, COLMAJ, Epi>(x, tc, lw, cs, s0, fix, epi, tid, nthreads)
     if (first && last) {
         if (K == 4) P2G_ROUND(4, true, true);
         else if (K == 3) P2G_ROUND(3, true, true);

@@ -17,6 +17,17 @@ enum { MAX_TILE_LOG = 11, WIDE_TILE_LOG = 10 };
 static inline __host__ __device__ unsigned tile_width_log(unsigned field_wlog, unsigned log_np) {
     return log_np > WIDE_TILE_LOG ? field_wlog - (log_np - WIDE_TILE_LOG) : field_wlog;
 }
+// The two final tile kinds keep their tile COLUMN-major (element (i, w) at x[w * cs + i]): the interleaved transforms of
+// such a tile are contiguous runs of global memory, so each arrives as ONE bulk copy of the TMA unit (cp.async.bulk,
+// ntt.cu) instead of np element-sized LDGSTS.  cs = np + pad: the pad spreads the 2^lw columns over the 32 banks (lanes
+// take consecutive w, then consecutive i: conflict-free for 8-byte words with pad = 16 >> lw, for 4-byte words with
+// 32 >> lw) and keeps every column 16-byte aligned, which the bulk copy requires (BabyBear at 16 columns: pad 4, 2-way).
+static inline __host__ __device__ unsigned tile_col_stride(unsigned elem_bytes, unsigned log_np, unsigned lw) {
+    unsigned pad = (128u / elem_bytes) >> lw;
+    const unsigned min_pad = 16u / elem_bytes;
+    if (pad < min_pad) pad = min_pad;
+    return (1u << log_np) + pad;
+}
 enum { POW_DIGIT_LOG = 10, POW_DIGIT = 1 << POW_DIGIT_LOG, POW_LEVELS = 3 };
 
 // ---- hash.cu -----------------------------------------------------------------------------------
