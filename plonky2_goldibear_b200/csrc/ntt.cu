@@ -43,6 +43,7 @@ struct NttGl {
     static const int W_LOG = 3;  // 8 x 8 B = 64-byte runs
     static const bool LIMBS = true;
     static const int MIN_CTAS = P2G_NTT_GL_MIN_CTAS;
+    static const unsigned TW_PREFETCH = 0;  // inter-pass factors fetched ahead of a unit's arithmetic (ntt_tile.cuh, StridedEpi)
     static __device__ __forceinline__ E load_user(E x) { return x; }
     static __device__ __forceinline__ E store_user(E x) { return gl_canon(x); }
     static __device__ __forceinline__ E mul(E a, E b) { return gl_mul(a, b); }
@@ -55,6 +56,7 @@ struct NttBb {
     static const int W_LOG = 4;  // 16 x 4 B = 64-byte runs
     static const bool LIMBS = false;
     static const int MIN_CTAS = 3;
+    static const unsigned TW_PREFETCH = 16;
     // The transforms are linear and every twiddle / coset factor / scale is a Montgomery-form constant, so
     // mul(word, constant) = word * constant in the WORD's own representation: canonical words go through the passes as
     // canonical words and Montgomery words as Montgomery words -- no conversion on the way in or out, only the range

@@ -284,9 +284,14 @@ struct StridedEpi {
     E *dst;
     const E *tw;
     u32 lp, lw, lmo, jt;
+    // F::TW_PREFETCH of a unit's factors are fetched before its arithmetic, the rest at the store: registers against
+    // latency.  Goldilocks 0 (a 16-point unit already holds 64 limb registers; fetching all 16 factors ahead costs 288
+    // bytes of spills per thread at 3 CTAs per SM: LDE of 2^20 x 135 17.70 ms, 8 ahead 17.64, none 17.40); BabyBear 16
+    // (2^22 x 256: 63.3 ms against 63.8 for 8 or none).
+    static const u32 NPRE = F::TW_PREFETCH;
     template <int K>
     struct Pre {
-        E t[1 << K];
+        E t[(1u << K) < NPRE ? (1u << K) : (NPRE ? NPRE : 1u)];
     };
     template <int K>
     P2G_TILE_FN size_t pos(u32 row0, u32 w, u32 s) const {
@@ -296,12 +301,15 @@ struct StridedEpi {
     template <int K, int KP>
     P2G_TILE_FN void prefetch(u32 row0, u32 w, Pre<KP> &pre) const {
 #pragma unroll
-        for (u32 s = 0; s < (1u << K) && s < (1u << KP); s++) pre.t[s] = tile_ldg(tw + pos<K>(row0, w, s));
+        for (u32 s = 0; s < (1u << K) && s < (1u << KP) && s < NPRE; s++) pre.t[s] = tile_ldg(tw + pos<K>(row0, w, s));
     }
     template <int K, int KP>
     P2G_TILE_FN void unit(u32 row0, u32 w, E (&v)[1 << K], const Pre<KP> &pre) const {
 #pragma unroll
-        for (u32 s = 0; s < (1u << K); s++) dst[pos<K>(row0, w, s)] = F::mul(v[s], pre.t[s]);  // internal repr
+        for (u32 s = 0; s < (1u << K); s++) {
+            const size_t o = pos<K>(row0, w, s);
+            dst[o] = F::mul(v[s], s < NPRE ? pre.t[s] : tile_ldg(tw + o));  // internal repr
+        }
     }
 };
 

@@ -22,6 +22,7 @@ struct GlH {
     typedef u64 E;
     static const int W_LOG = 3;
     static const bool LIMBS = true;
+    static const unsigned TW_PREFETCH = 0;
     static E load_user(E x) { return x; }
     static E store_user(E x) { return x >= GL_P ? x - GL_P : x; }
     static E mul(E a, E b) { return (u64)((u128)a * b % GL_P); }
@@ -42,6 +43,7 @@ struct BbH {
     typedef u32 E;
     static const int W_LOG = 4;
     static const bool LIMBS = false;
+    static const unsigned TW_PREFETCH = 16;
     static u32 redc(u64 x) {
         u32 m = (u32)x * 0x77ffffffu;
         u64 t = x + (u64)m * BB_P;
