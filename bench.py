@@ -190,8 +190,9 @@ def workload_config(args, field_name):
             "field": field_name, "log_rows": args.log_n, "cols": args.cols, "rate_bits": args.rate_bits,
             "cap_height": args.cap_height, "parallelism": "coset-sharded x%d" % args.gpus if args.gpus > 1 else "single GPU",
             "exchange": (args.exchange if args.gpus > 1 else None),
-            "exchange_transport": ((os.environ.get("P2G_EXCHANGE") or ("fused peer stores" if args.gpus == 2 else "block push kernel behind the inverse NTT"))
-                                   if args.gpus > 1 and args.exchange in ("fused", "pipelined") else None),
+            "exchange_transport": (("copy engines, one block per rank and ring step, under the LDE of the blocks already in" if args.exchange == "ring" else
+                                    (os.environ.get("P2G_EXCHANGE") or ("fused peer stores" if args.gpus == 2 else "block push kernel behind the inverse NTT")))
+                                   if args.gpus > 1 and args.exchange in ("fused", "pipelined", "ring") else None),
             "l2": "inputs (%.2f GB) and leaves (%.2f GB) are larger than the 126 MB L2; no flush needed" % (
                 args.cols * (1 << args.log_n) * (8 if field_name == "gl" else 4) / 1e9,
                 args.cols * ((1 << args.rate_bits) << args.log_n) * (8 if field_name == "gl" else 4) / 1e9)}
@@ -321,10 +322,15 @@ def run_ours(args, field_name, check_only=False):
     # (P2G_FLAG_LEAVES_READY).  Measured at 8 GPUs, 2^20 x 135: 21.1 ms (kernel stores) / 23.2 ms (copy engines) against
     # 20.4 ms for the plain fused exchange -- the extra barriers and smaller launches cost more than the overlap hides,
     # so "fused" stays the default.
+    # "ring": rank k's inverse NTT stays local; in step s = 1 .. G-1 its finished block goes to rank (k + s) % G through
+    # the copy engines (one source and one destination per rank and step, no SMs involved) while the main stream extends
+    # the block that arrived in step s-1 (its own block first) into the leaf matrix -- the LDE starts after 1/G of the
+    # coefficients has crossed NVLink instead of after all of it.  Blocks are whole NTT column tiles (sharding.ring_blocks).
     exchange = args.exchange if G > 1 else "none"
     pipelined = exchange in ("pipelined", "pipelined-ce")
+    ring = exchange == "ring"
     ce_copies = exchange == "pipelined-ce"  # peers receive the group through the copy engines instead of kernel stores
-    if pipelined:
+    if pipelined or ring:
         exchange = "fused"
     gather_ptrs, peer_tables, flag = [], [], None
     if exchange == "fused":
@@ -361,14 +367,19 @@ def run_ours(args, field_name, check_only=False):
         if int(ok) == 0:
             exchange = "nccl"
     pipelined = pipelined and exchange == "fused"
+    ring = ring and exchange == "fused"
     step_no = [0]
 
     # ---- pipelined exchange: column groups and who owns what.  Group s = columns [s*Wg, (s+1)*Wg); inside it rank k owns
     # the k-th slice of Wg/G columns (whole NTT tiles), so a group's columns are contiguous in the gather buffer.
-    if pipelined:
-        from plonky2_goldibear_b200.sharding import column_groups
-        group_ranges, owned = column_groups(c, G, 8 if field_name == "gl" else 16)
-        own_ranges = owned[rank]
+    if pipelined or ring:
+        from plonky2_goldibear_b200.sharding import column_groups, ring_blocks
+        if ring:
+            group_ranges = ring_blocks(c, G, 8 if field_name == "gl" else 16)  # block k = rank k's columns
+            own_ranges = [group_ranges[rank]]
+        else:
+            group_ranges, owned = column_groups(c, G, 8 if field_name == "gl" else 16)
+            own_ranges = owned[rank]
         own_total = sum(hi - lo for lo, hi in own_ranges)
         p_host = ctx.pinned_empty((max(own_total, 1), n), F.dtype)
         loc = 0
@@ -383,6 +394,7 @@ def run_ours(args, field_name, check_only=False):
             p_vals[:own_total].copy_(torch.from_numpy(p_host[:own_total].view(np.int64 if es == 8 else np.int32)))
         stream.synchronize()
         ev_g = [torch.cuda.Event() for _ in group_ranges]
+        ev_step_done = torch.cuda.Event()
         g_tbls, g_descs = [], []
         for glo, ghi in group_ranges:
             gd = make_desc(1, _lib.FLAG_DEVICE_INPUT | _lib.FLAG_DEVICE_OUTPUT | _lib.FLAG_LEAVES_ONLY)
@@ -424,6 +436,40 @@ def run_ours(args, field_name, check_only=False):
         ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(tree_desc)))
         kernel_s[:] += np.array(list(tree_desc.kernel_seconds))
 
+    def peer_ptr(k, rr):  # rank rr's gather buffer k as mapped here (peer_tables: own first, then the others in rank order)
+        return peer_tables[k][0 if rr == rank else 1 + (rr if rr < rank else rr - 1)]
+
+    def ring_step():
+        k = step_no[0] & 1
+        step_no[0] += 1
+        lo, hi = own_ranges[0]
+        # the exchange side of a commit starts when the previous commit of this rank is through (no run-ahead into the
+        # previous step's hashing: a step is one commit's own schedule, and a peer may only overwrite a gather buffer
+        # this rank has finished reading)
+        if step_no[0] > 1:
+            stream2.wait_event(ev_step_done)
+        if hi > lo:
+            ctx2.check(ctx2.lib.p2g_intt_allgather(ctx2.handle, F.field_id, 0, L, hi - lo, lo, p_vals.data_ptr(), peer_tables[k], 1))
+        ev_g[0].record(stream2)
+        off, nb = lo * n * es, (hi - lo) * n * es
+        for s_ in range(1, G):
+            if nb:
+                ctx2.check(ctx2.lib.p2g_memcpy_async(ctx2.handle, peer_ptr(k, (rank + s_) % G) + off, gather_ptrs[k] + off, nb, 2))
+            with torch.cuda.stream(stream2):
+                dist.all_reduce(flag)  # every rank's copy of this step has landed
+                ev_g[s_].record(stream2)
+        for s_ in range(G):
+            src = (rank - s_) % G
+            stream.wait_event(ev_g[s_])
+            glo, ghi = group_ranges[src]
+            if ghi > glo:
+                g_tbls[src][0] = gather_ptrs[k] + glo * n * es
+                ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(g_descs[src])))
+                kernel_s[:] += np.array(list(g_descs[src].kernel_seconds))
+        ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(tree_desc)))
+        kernel_s[:] += np.array(list(tree_desc.kernel_seconds))
+        ev_step_done.record(stream)
+
     def exchange_coeffs(d2h_slice=None):
         """inverse NTT of this rank's columns + all-gather; returns the device pointer holding all coefficients"""
         if exchange == "fused":
@@ -456,6 +502,8 @@ def run_ours(args, field_name, check_only=False):
     keep.append(coeff_tbl)
 
     def device_step():
+        if ring:
+            return ring_step()
         if pipelined:
             return pipelined_step()
         if G > 1:
@@ -488,14 +536,14 @@ def run_ours(args, field_name, check_only=False):
     for _ in range(0 if check_only else args.warmup):
         device_step()
     kernel_s[:] = 0
-    launches0 = ctx.kernel_launches() + (ctx2.kernel_launches() if pipelined else 0)
+    launches0 = ctx.kernel_launches() + (ctx2.kernel_launches() if (pipelined or ring) else 0)
     sampler = ClockSampler(local_rank)
     if rank == 0 and not check_only:
         sampler.start()
     dev_total, _ = timed(device_step, 1 if check_only else args.steps)
     clocks = sampler.stop() if rank == 0 and not check_only else None
-    launches = ctx.kernel_launches() + (ctx2.kernel_launches() if pipelined else 0) - launches0
-    args.exchange = ("pipelined-ce" if ce_copies else "pipelined") if pipelined else (exchange if G > 1 else None)  # what actually ran
+    launches = ctx.kernel_launches() + (ctx2.kernel_launches() if (pipelined or ring) else 0) - launches0
+    args.exchange = "ring" if ring else ("pipelined-ce" if ce_copies else "pipelined") if pipelined else (exchange if G > 1 else None)  # what actually ran
     t_step = dev_total / args.steps
     ksec = kernel_s / args.steps
     value = (c << L) / t_step
@@ -980,7 +1028,7 @@ def main():
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "pipelined", "pipelined-ce", "nccl"],
+    ap.add_argument("--exchange", default="fused", choices=["fused", "ring", "pipelined", "pipelined-ce", "nccl"],
                     help="multi-GPU coefficient exchange: inverse NTT with the all-gather fused into its epilogue over "
                          "peer memory (default); the same in column groups overlapped with the LDE (pipelined: kernel "
                          "stores, pipelined-ce: copy engines; both measured slower, DESIGN.md section 5); or a separate ncclAllGather")

@@ -70,3 +70,21 @@ def column_groups(num_cols: int, world: int, tile_cols: int):
     groups = [(lo, min(lo + wg, num_cols)) for lo in range(0, num_cols, wg)]
     owned = [[(min(glo + k * t, ghi), min(glo + (k + 1) * t, ghi)) for glo, ghi in groups] for k in range(world)]
     return groups, owned
+
+
+def ring_blocks(num_cols: int, world: int, tile_cols: int):
+    """Column blocks of the ring exchange (bench.py --exchange ring, the multi-device context): rank k owns the inverse NTT
+    of block k, a run of whole NTT column tiles (the last one may be ragged), blocks differ by at most one tile.  In step
+    s = 1 .. world-1 rank k sends its finished block to rank (k + s) % world and extends the block it received from rank
+    (k - s) % world into its leaf matrix, so the LDE starts after 1/world of the coefficients has arrived.
+    Returns [(lo, hi)] per rank."""
+    if world <= 0 or world & (world - 1):
+        raise ValueError("world size must be a power of two")
+    tiles = (num_cols + tile_cols - 1) // tile_cols
+    base, rem = divmod(tiles, world)
+    out, t = [], 0
+    for k in range(world):
+        take = base + (1 if k < rem else 0)
+        out.append((min(t * tile_cols, num_cols), min((t + take) * tile_cols, num_cols)))
+        t += take
+    return out
