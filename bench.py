@@ -439,6 +439,8 @@ def run_ours(args, field_name, check_only=False):
     def peer_ptr(k, rr):  # rank rr's gather buffer k as mapped here (peer_tables: own first, then the others in rank order)
         return peer_tables[k][0 if rr == rank else 1 + (rr if rr < rank else rr - 1)]
 
+    ring_events = []
+
     def ring_step():
         k = step_no[0] & 1
         step_no[0] += 1
@@ -458,14 +460,27 @@ def run_ours(args, field_name, check_only=False):
             with torch.cuda.stream(stream2):
                 dist.all_reduce(flag)  # every rank's copy of this step has landed
                 ev_g[s_].record(stream2)
+        # the LDE split by pass (p2g_lde_columns): the strided passes of a block as soon as it is in, the last pass -- which
+        # writes whole leaf rows -- once over all columns (a split by column range, P2G_FLAG_LEAVES_ONLY per block, makes
+        # every block write a narrow strip of every row: 16-column blocks cost the LDE +36..49 %, tools/lde_blocks_probe.py)
+        shard = (rank, G)
         for s_ in range(G):
             src = (rank - s_) % G
             stream.wait_event(ev_g[s_])
             glo, ghi = group_ranges[src]
             if ghi > glo:
-                g_tbls[src][0] = gather_ptrs[k] + glo * n * es
-                ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(g_descs[src])))
-                kernel_s[:] += np.array(list(g_descs[src].kernel_seconds))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                ctx.check(ctx.lib.p2g_lde_columns(ctx.handle, F.field_id, 0, L, r, shard[0], shard[1], c, glo, ghi - glo,
+                                                  gather_ptrs[k] + glo * n * es, None, 0, 0))
+                e1.record(stream)
+                ring_events.append((e0, e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.check(ctx.lib.p2g_lde_columns(ctx.handle, F.field_id, 0, L, r, shard[0], shard[1], c, 0, c, gather_ptrs[k],
+                                          d_leaves.data_ptr(), c, 1))
+        e1.record(stream)
+        ring_events.append((e0, e1))
         ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(tree_desc)))
         kernel_s[:] += np.array(list(tree_desc.kernel_seconds))
         ev_step_done.record(stream)
@@ -536,12 +551,15 @@ def run_ours(args, field_name, check_only=False):
     for _ in range(0 if check_only else args.warmup):
         device_step()
     kernel_s[:] = 0
+    del ring_events[:]
     launches0 = ctx.kernel_launches() + (ctx2.kernel_launches() if (pipelined or ring) else 0)
     sampler = ClockSampler(local_rank)
     if rank == 0 and not check_only:
         sampler.start()
     dev_total, _ = timed(device_step, 1 if check_only else args.steps)
     clocks = sampler.stop() if rank == 0 and not check_only else None
+    if ring:
+        kernel_s[1] += sum(a.elapsed_time(b) for a, b in ring_events) * 1e-3  # the LDE passes, without the waits between them
     launches = ctx.kernel_launches() + (ctx2.kernel_launches() if (pipelined or ring) else 0) - launches0
     args.exchange = "ring" if ring else ("pipelined-ce" if ce_copies else "pipelined") if pipelined else (exchange if G > 1 else None)  # what actually ran
     t_step = dev_total / args.steps

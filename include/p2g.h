@@ -258,6 +258,24 @@ int32_t p2g_memcpy_async(p2g_ctx *ctx, void *dst, const void *src, size_t bytes,
 int32_t p2g_intt_allgather(p2g_ctx *ctx, int32_t field, int32_t repr, uint32_t log_n, uint32_t num_cols, uint32_t col_offset,
                            const void *values_dev, void *const *gather_bufs, uint32_t num_bufs);
 
+/* The LDE of one shard split by NTT PASS, for multi-GPU pipelines in which the coefficient columns arrive block by
+ * block (bench.py --exchange ring).  A commit split by column RANGE (P2G_FLAG_LEAVES_ONLY) makes every block write a narrow
+ * strip of every leaf row, which costs the last pass its write locality (16-column blocks: +36..49 % LDE time on one GPU,
+ * tools/lde_blocks_probe.py); here only the strided passes (column-major scratch inside the context) run per block and
+ * the last pass writes whole leaf rows once:
+ *   phase P2G_LDE_STRIDED: coeffs_dev = [num_cols][n] coefficients (device) of columns [col_base, col_base + num_cols)
+ *                          of a batch of total_cols; leaves_dev unused.  No-op for sizes whose transform is one pass.
+ *   phase P2G_LDE_LAST   : after every column had its STRIDED call: col_base = 0, num_cols = total_cols; writes the
+ *                          shard's rows (all of its cosets) to leaves_dev at leaf_pitch.  coeffs_dev = all total_cols
+ *                          columns (read by single-pass sizes only).
+ * Asynchronous on the context's stream; P2G_FLAG_LEAVES_READY builds the tree afterwards.  The scratch is only valid
+ * until the context's next transform, so no other call may come between the STRIDED calls and the LAST one. */
+#define P2G_LDE_STRIDED 0
+#define P2G_LDE_LAST 1
+int32_t p2g_lde_columns(p2g_ctx *ctx, int32_t field, int32_t repr, uint32_t log_n, uint32_t rate_bits, uint32_t shard_index,
+                        uint32_t shard_count, uint32_t total_cols, uint32_t col_base, uint32_t num_cols, const void *coeffs_dev,
+                        void *leaves_dev, uint64_t leaf_pitch, int32_t phase);
+
 /* Device workspace currently held by the context (bytes) and a way to drop it. */
 uint64_t p2g_workspace_bytes(p2g_ctx *ctx);
 void p2g_release_workspace(p2g_ctx *ctx);

@@ -52,7 +52,7 @@ EXPORTS = [
     "p2g_merkle", "p2g_merkle_finish_cap", "p2g_permute", "p2g_transform", "p2g_workspace_bytes",
     "p2g_release_workspace", "p2g_stream", "p2g_kernel_launches", "p2g_batch_get_rows", "p2g_batch_prove",
     "p2g_batch_download", "p2g_batch_shape", "p2g_batch_free", "p2g_dev_alloc", "p2g_dev_free", "p2g_ipc_export",
-    "p2g_ipc_import", "p2g_ipc_close", "p2g_intt_allgather", "p2g_memcpy_async",
+    "p2g_ipc_import", "p2g_ipc_close", "p2g_intt_allgather", "p2g_lde_columns", "p2g_memcpy_async",
     "p2g_fri_begin", "p2g_fri_commit_layer", "p2g_fri_fold", "p2g_fri_finish", "p2g_fri_shape", "p2g_fri_free", "p2g_fri_pow",
     "p2g_num_devices", "p2g_sub_context",
 ]
@@ -126,6 +126,8 @@ def load_library() -> ctypes.CDLL:
         lib.p2g_ipc_close.restype = i32
         lib.p2g_intt_allgather.argtypes = [vp, i32, i32, u32, u32, u32, vp, ctypes.POINTER(vp), u32]
         lib.p2g_intt_allgather.restype = i32
+        lib.p2g_lde_columns.argtypes = [vp, i32, i32, u32, u32, u32, u32, u32, u32, u32, vp, vp, u64, i32]
+        lib.p2g_lde_columns.restype = i32
         lib.p2g_memcpy_async.argtypes = [vp, vp, vp, ctypes.c_size_t, i32]
         lib.p2g_memcpy_async.restype = i32
         lib.p2g_fri_begin.argtypes = [vp, i32, i32, i32, u32, u32, vp, vp, u32, ctypes.POINTER(vp)]

@@ -381,9 +381,14 @@ static int exchange_mode(unsigned num_peers, bool sendable) {  // sendable: one 
 //            shifts[b], rows written to the leaf matrix `dst` starting at row_base + b * row_stride.
 // `src` is overwritten when inverse (the strided passes run in place); forward uses `tmp` for the strided passes
 // (nb * num_cols * n elements).
+// pass_mode (forward only; the split LDE of p2g_lde_columns): 0 = every pass; 1 = the strided passes only, of the
+// num_cols columns at `src`, into column slots [tmp_col_base, ...) of a scratch that is tmp_cols_total columns wide per
+// coset; 2 = the last pass only, over num_cols = tmp_cols_total columns whose strided passes were run before (`src` is
+// read by single-pass sizes only, which have no strided pass).
 int run_transform_batch(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse, unsigned log_n, unsigned num_cols,
                         void *src, void *tmp, void *dst, uint64_t dst_stride, const uint64_t *shifts, unsigned nb,
-                        uint64_t row_base, uint64_t row_stride, void *const *peer_dst = nullptr, unsigned num_peers = 0) {
+                        uint64_t row_base, uint64_t row_stride, void *const *peer_dst = nullptr, unsigned num_peers = 0,
+                        int pass_mode = 0, uint64_t tmp_cols_total = 0, uint64_t tmp_col_base = 0) {
     unsigned lps[3], P;
     plan_passes(log_n, lps, &P);
     const uint64_t n = (uint64_t)1 << log_n;
@@ -393,6 +398,8 @@ int run_transform_batch(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse
     const void *cur_src = src;
     uint64_t cur_src_batch_stride = 0;
     void *stage_buf = inverse ? src : tmp;
+    const uint64_t stage_cols = tmp_cols_total ? tmp_cols_total : num_cols;  // columns per coset in the scratch
+    if (pass_mode && !inverse) stage_buf = (char *)tmp + (size_t)tmp_col_base * n * f.elem;
     for (unsigned i = 0; i < P; i++) {
         NttPass p;
         memset(&p, 0, sizeof p);
@@ -423,11 +430,13 @@ int run_transform_batch(p2g_ctx *ctx, const FieldInfo &f, int repr, bool inverse
                 if ((rc = get_pass_table(ctx, f, 0, log_min, lps[i], w, (i == 0 && !inverse) ? shifts[b] : 0, &p.tw_tables[b]))) return rc;
             p.dst = stage_buf;
             p.dst_col_stride = n;
-            p.dst_batch_stride = (uint64_t)num_cols * n;
-            launch_ntt_pass(f.id, repr, NTT_STRIDED, p, ctx->stream, &ctx->launches);
+            p.dst_batch_stride = stage_cols * n;
+            if (pass_mode != 2) launch_ntt_pass(f.id, repr, NTT_STRIDED, p, ctx->stream, &ctx->launches);
             cur_src = stage_buf;
-            cur_src_batch_stride = (uint64_t)num_cols * n;
+            cur_src_batch_stride = stage_cols * n;
             log_min -= lps[i];
+        } else if (pass_mode == 1) {
+            break;  // the last pass follows in a later call, over all columns
         } else {
             p.lp1 = P >= 2 ? lps[0] : 0;
             p.lp2 = P >= 3 ? lps[1] : 0;
@@ -2151,6 +2160,42 @@ int32_t p2g_intt_allgather(p2g_ctx *ctx, int32_t field, int32_t repr, uint32_t l
     if ((rc = run_transform(ctx, f, repr, true, log_n, num_cols, ctx->in.ptr, nullptr, own, n, 0, 0, peers, num_bufs - 1))) return rc;
     // asynchronous on the context's stream: the caller orders the cross-GPU barrier and the commit behind it
     return P2G_OK;
+}
+
+// The LDE of a shard split by PASS (see p2g.h): the strided passes column block by column block, as the blocks arrive,
+// and the last pass -- which writes the leaf rows -- once over all columns.
+int32_t p2g_lde_columns(p2g_ctx *ctx, int32_t field, int32_t repr, uint32_t log_n, uint32_t rate_bits, uint32_t shard_index,
+                        uint32_t shard_count, uint32_t total_cols, uint32_t col_base, uint32_t num_cols, const void *coeffs_dev,
+                        void *leaves_dev, uint64_t leaf_pitch, int32_t phase) {
+    if (!ctx) return P2G_ERR_NO_DEVICE;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (field != P2G_FIELD_GOLDILOCKS && field != P2G_FIELD_BABYBEAR) return ctx->fail(P2G_ERR_UNSUPPORTED, "unknown field");
+    const FieldInfo &f = field == P2G_FIELD_GOLDILOCKS ? kGl : kBb;
+    if (f.id == FIELD_GL) repr = 0;
+    const unsigned G = shard_count ? shard_count : 1, gi = shard_count ? shard_index : 0;
+    if ((G & (G - 1)) || gi >= G) return ctx->fail(P2G_ERR_INVALID, "bad shard");
+    const unsigned lg = ilog2(G), L = log_n, r = rate_bits, LN = L + r;
+    if (lg > r) return ctx->fail(P2G_ERR_UNSUPPORTED, "shard_count %u exceeds the 2^rate_bits = %u cosets", G, 1u << r);
+    if (LN > f.two_adicity || LN > 30 || L > 3 * MAX_TILE_LOG) return ctx->fail(P2G_ERR_INVALID, "LDE size 2^%u unsupported", LN);
+    if (phase != P2G_LDE_STRIDED && phase != P2G_LDE_LAST) return ctx->fail(P2G_ERR_INVALID, "bad phase");
+    if (!total_cols || !num_cols || (uint64_t)col_base + num_cols > total_cols) return ctx->fail(P2G_ERR_INVALID, "bad column range");
+    if (phase == P2G_LDE_LAST && (col_base || num_cols != total_cols || !leaves_dev || leaf_pitch < total_cols))
+        return ctx->fail(P2G_ERR_INVALID, "the last pass covers all columns and needs the leaf rows");
+    const uint64_t n = (uint64_t)1 << L;
+    const unsigned cosets_local = (1u << r) >> lg, coset0 = gi * cosets_local;
+    const bool multi = multi_pass(L);
+    if ((multi ? phase == P2G_LDE_STRIDED : phase == P2G_LDE_LAST) && !coeffs_dev) return ctx->fail(P2G_ERR_INVALID, "coeffs_dev is NULL");
+    if (!multi && phase == P2G_LDE_STRIDED) return P2G_OK;  // a single-pass transform has no strided pass
+    int rc;
+    // every coset of the shard in one launch per pass; the scratch holds the strided passes' output of all of them
+    if (multi && (rc = ensure(ctx, ctx->tmp, (size_t)cosets_local * total_cols * n * f.elem))) return rc;
+    uint64_t shifts[8];
+    const uint64_t wN = two_adic_generator(f, LN);
+    for (unsigned k = 0; k < cosets_local; k++) shifts[k] = f_mul(f, f.generator, f_pow(f, wN, bitrev(coset0 + k, r)));
+    return run_transform_batch(ctx, f, repr, false, L, num_cols, const_cast<void *>(coeffs_dev), ctx->tmp.ptr, leaves_dev, leaf_pitch,
+                               shifts, cosets_local, 0, n, nullptr, 0, phase == P2G_LDE_STRIDED ? 1 : 2, total_cols, col_base);
 }
 
 }  // extern "C"

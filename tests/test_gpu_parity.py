@@ -576,6 +576,63 @@ def test_commit_split_over_column_ranges(ctx, oracle, field, log_n, c, r, h, g, 
             assert (d_dig.cpu().numpy().view(F.dtype)[:len(one.merkle_tree.digests)] == one.merkle_tree.digests).all()
 
 
+@pytest.mark.parametrize("field,log_n,c,r,h,g,tile_log", [(0, 12, 19, 3, 4, 1, 0), (0, 12, 135, 3, 4, 8, 0), (0, 9, 21, 3, 4, 4, 0),
+                                                          (1, 13, 40, 3, 4, 2, 0), (0, 12, 11, 2, 2, 2, 4), (1, 12, 33, 3, 3, 4, 5)])
+def test_lde_split_by_pass(ctx, oracle, monkeypatch, field, log_n, c, r, h, g, tile_log):
+    """p2g_lde_columns: the strided passes block by block in the order a ring exchange delivers the blocks (own block
+    first, then the others), the last pass once over all columns, then the tree (P2G_FLAG_LEAVES_READY) -- leaves,
+    digests and cap of every shard equal the oracle's.  Covers one-, two- and (through the tile-size hook) three-pass
+    plans, ragged and empty blocks, several cosets per shard."""
+    import ctypes
+    import torch
+    from plonky2_goldibear_b200 import _lib
+    from plonky2_goldibear_b200.sharding import ring_blocks
+    if tile_log:
+        monkeypatch.setenv("P2G_TEST_MAX_TILE_LOG", str(tile_log))
+    F = fields()[field]
+    n, N = 1 << log_n, 1 << (log_n + r)
+    vals = synthetic_columns(F.order, F.dtype, c, n, seed=35)
+    ref = oracle.commit(field, vals, oracle.VALUES, r, h)
+    coeffs = np.ascontiguousarray(ref["coeffs"])
+    tdt, ndt = (torch.int64, np.int64) if field == 0 else (torch.int32, np.int32)
+    d_el = F.num_hash_out_elts
+    lg = g.bit_length() - 1
+    rows_local, cap_local = N // g, max(h - lg, 0)
+    d_coeffs = torch.from_numpy(coeffs.view(ndt)).cuda()
+    blocks = ring_blocks(c, max(g, 4), 8 if field == 0 else 16)
+    es = F.elem_bytes
+    nd, per_cap = len(ref["digests"]) // g, (1 << h) // g
+    for shard in range(g):
+        d_leaves = torch.zeros((rows_local, c + 3), dtype=tdt, device="cuda")  # a pitch wider than the rows
+        d_dig = torch.zeros((max(2 * (rows_local - (1 << cap_local)), 1), d_el), dtype=tdt, device="cuda")
+        d_cap = torch.zeros((1 << cap_local, d_el), dtype=tdt, device="cuda")
+        torch.cuda.synchronize()
+        order = [(shard - s) % len(blocks) for s in range(len(blocks))]
+        for b in order:
+            lo, hi = blocks[b]
+            if hi > lo:
+                ctx.check(ctx.lib.p2g_lde_columns(ctx.handle, F.field_id, 0, log_n, r, shard, g if g > 1 else 0, c, lo, hi - lo,
+                                                  d_coeffs.data_ptr() + lo * n * es, None, 0, 0))
+        ctx.check(ctx.lib.p2g_lde_columns(ctx.handle, F.field_id, 0, log_n, r, shard, g if g > 1 else 0, c, 0, c,
+                                          d_coeffs.data_ptr(), d_leaves.data_ptr(), c + 3, 1))
+        d = _lib.CommitDesc()
+        d.field, d.hash, d.repr, d.input_kind = F.field_id, F.hash_id, 0, 1
+        d.log_n, d.num_cols, d.rate_bits, d.cap_height = log_n, c, r, h
+        d.flags = _lib.FLAG_DEVICE_INPUT | _lib.FLAG_DEVICE_OUTPUT | _lib.FLAG_LEAVES_READY
+        d.shard_index, d.shard_count = (shard, g) if g > 1 else (0, 0)
+        d.leaf_pitch = c + 3
+        d.leaves_out, d.digests_out, d.cap_out = d_leaves.data_ptr(), d_dig.data_ptr(), d_cap.data_ptr()
+        ctx.check(ctx.lib.p2g_commit(ctx.handle, ctypes.byref(d)))
+        torch.cuda.synchronize()
+        r0 = shard * rows_local
+        assert (d_leaves.cpu().numpy().view(F.dtype)[:, :c] == ref["leaves"][r0:r0 + rows_local]).all()
+        assert (d_dig.cpu().numpy().view(F.dtype)[:nd] == ref["digests"][shard * nd:(shard + 1) * nd]).all()
+        assert (d_cap.cpu().numpy().view(F.dtype) == ref["cap"][shard * per_cap:(shard + 1) * per_cap]).all()
+    # misuse is refused
+    assert ctx.lib.p2g_lde_columns(ctx.handle, F.field_id, 0, log_n, r, 0, 0, c, 1, c, d_coeffs.data_ptr(), None, 0, 0) != 0
+    assert ctx.lib.p2g_lde_columns(ctx.handle, F.field_id, 0, log_n, r, 0, 0, c, 0, c, d_coeffs.data_ptr(), None, 0, 1) != 0
+
+
 def ctx_commit_shard(ctx, F, vals, r, h, shard, g):
     import plonky2_goldibear_b200 as p2g
     return p2g.PolynomialBatch.from_values(F, list(vals), r, False, h, ctx=ctx, shard_index=shard, shard_count=g)

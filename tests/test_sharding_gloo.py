@@ -154,3 +154,82 @@ def test_two_rank_pipelined_exchange_by_column_groups(tmp_path, oracle):
         db, de, cb, ce = [int(x) for x in p["plan"]]
         assert (ref["digests"][db:de] == p["digests"]).all()
         assert (ref["cap"][cb:ce] == p["cap"]).all()
+
+
+def test_ring_exchange_blocks_and_schedule():
+    """bench.py --exchange ring: blocks partition the columns into runs of whole NTT column tiles that differ by at most
+    one tile; in step s rank k sends block k to rank (k + s) % G and receives block (k - s) % G, so after G - 1 steps
+    every rank holds every block exactly once."""
+    from plonky2_goldibear_b200.sharding import ring_blocks
+    for c, world, tile in ((135, 8, 8), (135, 4, 8), (135, 2, 8), (256, 8, 16), (256, 2, 16), (5, 8, 8), (64, 8, 8), (1, 1, 8), (17, 4, 8)):
+        blocks = ring_blocks(c, world, tile)
+        assert len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == c
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        assert all(lo % tile == 0 or lo == c for lo, _ in blocks)
+        tiles = [-(-(hi - lo) // tile) for lo, hi in blocks]
+        assert max(tiles) - min(tiles) <= 1
+        for k in range(world):
+            got = [k] + [(k - s) % world for s in range(1, world)]   # own block, then one per step
+            assert sorted(got) == list(range(world))
+            for s in range(1, world):
+                assert ((k - s) % world + s) % world == k             # the sender of step s targets this rank
+    assert ring_blocks(135, 8, 8) == [(0, 24), (24, 40), (40, 56), (56, 72), (72, 88), (88, 104), (104, 120), (120, 135)]
+
+
+def _ring_worker(rank, world, port, log_n, c, r, h, tile, out_dir):
+    """The ring exchange on CPU: own inverse NTT, then per step one block out / one block in (point to point), the LDE of
+    each block written into its column range as soon as it is in, the tree at the end."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch
+    from oracle import p2o
+    from plonky2_goldibear_b200.sharding import plan, ring_blocks
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 1 << log_n
+    sp = plan(rank, world, c, log_n, r, h)
+    blocks = ring_blocks(c, world, tile)
+    leaves = np.zeros((sp.row_end - sp.row_begin, c), dtype=np.uint64)
+
+    def extend(lo, hi, coeffs):
+        if hi > lo:
+            leaves[:, lo:hi] = p2o.commit(p2o.GL, coeffs, p2o.COEFFS, r, 0)["leaves"][sp.row_begin:sp.row_end]
+
+    lo, hi = blocks[rank]
+    mine = synthetic_columns(GL_P, np.uint64, hi - lo, n, col_begin=lo) if hi > lo else np.zeros((0, n), dtype=np.uint64)
+    own = np.stack([p2o.ifft(p2o.GL, v) for v in mine]) if hi > lo else mine
+    extend(lo, hi, own)
+    for s in range(1, world):
+        dst, src = (rank + s) % world, (rank - s) % world
+        slo, shi = blocks[src]
+        out_t = torch.from_numpy(own.view(np.int64).copy())
+        in_t = torch.zeros((shi - slo, n), dtype=torch.int64)
+        reqs = []
+        if hi > lo:
+            reqs.append(dist.isend(out_t, dst))
+        if shi > slo:
+            reqs.append(dist.irecv(in_t, src))
+        for q in reqs:
+            q.wait()
+        extend(slo, shi, in_t.numpy().view(np.uint64))
+    digests, cap = p2o.merkle_tree(p2o.GL, leaves, sp.local_cap_height)
+    np.savez(os.path.join(out_dir, "rrank%d.npz" % rank), rows=leaves, digests=digests, cap=cap,
+             plan=np.array([sp.digest_begin, sp.digest_end, sp.cap_begin, sp.cap_end]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_ring_exchange(tmp_path, oracle):
+    world, log_n, c, r, h, tile = 2, 5, 11, 2, 2, 2
+    port = _free_port()
+    mp.spawn(_ring_worker, args=(world, port, log_n, c, r, h, tile, str(tmp_path)), nprocs=world, join=True)
+    vals = synthetic_columns(GL_P, np.uint64, c, 1 << log_n)
+    ref = oracle.commit(oracle.GL, vals, oracle.VALUES, r, h)
+    parts = [np.load(os.path.join(str(tmp_path), "rrank%d.npz" % i)) for i in range(world)]
+    assert (np.concatenate([p["rows"] for p in parts]) == ref["leaves"]).all()
+    for p in parts:
+        db, de, cb, ce = [int(x) for x in p["plan"]]
+        assert (ref["digests"][db:de] == p["digests"]).all()
+        assert (ref["cap"][cb:ce] == p["cap"]).all()
