@@ -1046,10 +1046,13 @@ def main():
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "ring", "pipelined", "pipelined-ce", "nccl"],
-                    help="multi-GPU coefficient exchange: inverse NTT with the all-gather fused into its epilogue over "
-                         "peer memory (default); the same in column groups overlapped with the LDE (pipelined: kernel "
-                         "stores, pipelined-ce: copy engines; both measured slower, DESIGN.md section 5); or a separate ncclAllGather")
+    ap.add_argument("--exchange", default="ring", choices=["ring", "fused", "pipelined", "pipelined-ce", "nccl"],
+                    help="multi-GPU coefficient exchange: ring (default) -- each rank's finished block of coefficient columns "
+                         "goes round the ring through the copy engines while the strided LDE passes of the blocks already in "
+                         "run (p2g_lde_columns); fused -- inverse NTT with the all-gather in its epilogue / a push kernel "
+                         "behind it, the LDE after a barrier; the same in column groups overlapped with the LDE (pipelined: "
+                         "kernel stores, pipelined-ce: copy engines; both measured slower, DESIGN.md section 5); or a "
+                         "separate ncclAllGather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fri", action="store_true", help="skip the secondary FRI commit-phase measurement")
     ap.add_argument("--cpu-sample-log-n", type=int, default=16)
