@@ -301,14 +301,14 @@ struct StridedEpi {
     template <int K, int KP>
     P2G_TILE_FN void prefetch(u32 row0, u32 w, Pre<KP> &pre) const {
 #pragma unroll
-        for (u32 s = 0; s < (1u << K) && s < (1u << KP) && s < NPRE; s++) pre.t[s] = tile_ldg(tw + pos<K>(row0, w, s));
+        for (u32 s = 0; s < (1u << K) && s < (1u << KP) && (int)s < (int)NPRE; s++) pre.t[s] = tile_ldg(tw + pos<K>(row0, w, s));
     }
     template <int K, int KP>
     P2G_TILE_FN void unit(u32 row0, u32 w, E (&v)[1 << K], const Pre<KP> &pre) const {
 #pragma unroll
         for (u32 s = 0; s < (1u << K); s++) {
             const size_t o = pos<K>(row0, w, s);
-            dst[o] = F::mul(v[s], s < NPRE ? pre.t[s] : tile_ldg(tw + o));  // internal repr
+            dst[o] = F::mul(v[s], (int)s < (int)NPRE ? pre.t[s] : tile_ldg(tw + o));  // internal repr
         }
     }
 };
