@@ -233,3 +233,43 @@ def test_two_rank_ring_exchange(tmp_path, oracle):
         db, de, cb, ce = [int(x) for x in p["plan"]]
         assert (ref["digests"][db:de] == p["digests"]).all()
         assert (ref["cap"][cb:ce] == p["cap"]).all()
+
+
+def test_final_tile_column_stride_is_bank_conflict_free():
+    """csrc/p2g_internal.h tile_col_stride: the column-major tile of the two final NTT kinds (x[w * cs + i], loaded by one
+    bulk copy per column) with the kernels' lane map (consecutive lanes take consecutive w, then consecutive units).  An
+    8-byte access is served per half-warp, a 4-byte access per warp; the stride must keep every such group on distinct
+    banks in all rounds but the last, and every column 16-byte aligned for cp.async.bulk.  (BabyBear tiles of 16 columns
+    cannot have both: they are 2-way conflicted)"""
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "plonky2_goldibear_b200", "csrc",
+                            "p2g_internal.h")).read()
+    assert "(128u / elem_bytes) >> lw" in hdr and "16u / elem_bytes" in hdr  # the formula restated below
+
+    def col_stride(elem, lp, lw):
+        pad = max((128 // elem) >> lw, 16 // elem)
+        return (1 << lp) + pad
+
+    def conflicts(elem, lp, lw, lowbits):
+        cs = col_stride(elem, lp, lw)
+        assert (cs * elem) % 16 == 0
+        group = 16 if elem == 8 else 32          # lanes served together
+        words = elem // 4
+        worst = 1
+        for first in range(0, 256, group):        # a CTA's threads, unit u = thread id
+            banks = {}
+            for u in range(first, first + group):
+                w, t = u & ((1 << lw) - 1), u >> lw
+                low, hi = t & ((1 << lowbits) - 1), t >> lowbits
+                p0 = (hi << (lowbits + 4)) | low  # a 16-point unit: its first point (the others are + j << lowbits)
+                addr_words = (w * cs + p0) * words
+                b = (addr_words % 32) // words
+                banks[b] = banks.get(b, 0) + 1
+            worst = max(worst, max(banks.values()))
+        return worst
+
+    for lp, lw in ((10, 3), (11, 2), (9, 3)):                 # Goldilocks: 8 columns up to 2^10 points, 4 at 2^11
+        for lowbits in (lp - 4, lp - 7):
+            assert conflicts(8, lp, lw, lowbits) == 1, (lp, lw, lowbits)
+    for lowbits in (7, 3):                                      # BabyBear 2^11 points x 8 columns (config 3)
+        assert conflicts(4, 11, 3, lowbits) == 1
+    assert conflicts(4, 10, 4, 6) == 2                          # BabyBear 16 columns: 2-way, as documented
