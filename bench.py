@@ -325,7 +325,7 @@ def run_ours(args, field_name, check_only=False):
     # "ring": rank k's inverse NTT stays local; in step s = 1 .. G-1 its finished block goes to rank (k + s) % G through
     # the copy engines (one source and one destination per rank and step, no SMs involved) while the main stream extends
     # the block that arrived in step s-1 (its own block first) into the leaf matrix -- the LDE starts after 1/G of the
-    # coefficients has crossed NVLink instead of after all of it.  Blocks are whole NTT column tiles (sharding.ring_blocks).
+    # coefficients has crossed NVLink instead of after all of it.  Blocks are even column shares (sharding.ring_blocks).
     exchange = args.exchange if G > 1 else "none"
     pipelined = exchange in ("pipelined", "pipelined-ce")
     ring = exchange == "ring"
@@ -375,7 +375,10 @@ def run_ours(args, field_name, check_only=False):
     if pipelined or ring:
         from plonky2_goldibear_b200.sharding import column_groups, ring_blocks
         if ring:
-            group_ranges = ring_blocks(c, G, 8 if field_name == "gl" else 16)  # block k = rank k's columns
+            # block k = rank k's columns.  Even shares to the column: the strided passes work column by column, and the last
+            # pass runs once over all columns, so a block need not be whole 8- / 16-column tiles; the ring steps are
+            # globally synchronised, i.e. every step lasts as long as the largest block's copy
+            group_ranges = ring_blocks(c, G, 1)
             own_ranges = [group_ranges[rank]]
         else:
             group_ranges, owned = column_groups(c, G, 8 if field_name == "gl" else 16)

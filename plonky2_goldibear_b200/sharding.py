@@ -73,8 +73,9 @@ def column_groups(num_cols: int, world: int, tile_cols: int):
 
 
 def ring_blocks(num_cols: int, world: int, tile_cols: int):
-    """Column blocks of the ring exchange (bench.py --exchange ring, the multi-device context): rank k owns the inverse NTT
-    of block k, a run of whole NTT column tiles (the last one may be ragged), blocks differ by at most one tile.  In step
+    """Column blocks of the ring exchange (bench.py --exchange ring): rank k owns the inverse NTT of block k, a run of whole
+    units of tile_cols columns (the last one may be ragged), blocks differ by at most one unit; tile_cols = 1 gives even
+    shares to the column, which is what the pass-split LDE (p2g_lde_columns) allows and bench.py uses.  In step
     s = 1 .. world-1 rank k sends its finished block to rank (k + s) % world and extends the block it received from rank
     (k - s) % world into its leaf matrix, so the LDE starts after 1/world of the coefficients has arrived.
     Returns [(lo, hi)] per rank."""

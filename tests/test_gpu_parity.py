@@ -599,7 +599,8 @@ def test_lde_split_by_pass(ctx, oracle, monkeypatch, field, log_n, c, r, h, g, t
     lg = g.bit_length() - 1
     rows_local, cap_local = N // g, max(h - lg, 0)
     d_coeffs = torch.from_numpy(coeffs.view(ndt)).cuda()
-    blocks = ring_blocks(c, max(g, 4), 8 if field == 0 else 16)
+    # odd column counts: even shares to the column (what bench.py uses); the others: whole NTT column tiles
+    blocks = ring_blocks(c, max(g, 4), 1 if c % 2 else (8 if field == 0 else 16))
     es = F.elem_bytes
     nd, per_cap = len(ref["digests"]) // g, (1 << h) // g
     for shard in range(g):

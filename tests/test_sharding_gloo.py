@@ -161,7 +161,7 @@ def test_ring_exchange_blocks_and_schedule():
     one tile; in step s rank k sends block k to rank (k + s) % G and receives block (k - s) % G, so after G - 1 steps
     every rank holds every block exactly once."""
     from plonky2_goldibear_b200.sharding import ring_blocks
-    for c, world, tile in ((135, 8, 8), (135, 4, 8), (135, 2, 8), (256, 8, 16), (256, 2, 16), (5, 8, 8), (64, 8, 8), (1, 1, 8), (17, 4, 8)):
+    for c, world, tile in ((135, 8, 8), (135, 4, 8), (135, 2, 8), (256, 8, 16), (256, 2, 16), (5, 8, 8), (64, 8, 8), (1, 1, 8), (17, 4, 8), (135, 8, 1), (135, 4, 1), (5, 8, 1)):
         blocks = ring_blocks(c, world, tile)
         assert len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == c
         assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
